@@ -1,0 +1,139 @@
+/*
+ * klt_b200.h -- C ABI of libklt_b200.so: B200 (sm_100a) pyramid build + pyramidal Lucas-Kanade.
+ *
+ * Drop-in boundary for the one hot path of JonasFrey96/Visual-Odom-Pipeline that this project
+ * replaces: the four `cv2.calcOpticalFlowPyrLK(im0, im1, p, None, winSize, maxLevel, criteria)`
+ * calls per frame at reference src/extractor/extractor.py:44,45 (extend_tracks) and :65,66
+ * (extend_landmarks), with parameters from src/extractor/extractor.py:16-19.  The reference has no
+ * plugin API for this path -- the interface *is* the OpenCV function -- so the entry points below
+ * are what a ctypes binding of that function (and of cv2.buildOpticalFlowPyramid, which OpenCV
+ * runs inside it) binds.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain C, no exceptions / STL / torch types across the ABI.  Every function returns
+ * a klt_status (0 = ok, <0 = KLT_ERR_*, >0 = cudaError_t passed through).  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Device pointers are owned by the
+ * caller.  Functions named *_host take HOST pointers, do their own H2D/D2H and are synchronous on
+ * return (like the cv2 call); all others are asynchronous on `stream`.
+ *
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef KLT_B200_H
+#define KLT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLT_B200_VERSION 100 /* 0.1.0 */
+
+#define KLT_MAX_LEVELS 16   /* pyramid levels incl. level 0 (cv2 stops when a level <= winSize) */
+#define KLT_MAX_WIN_AREA 4096 /* win_w * win_h supported by the LK kernel (cv2 default 21x21) */
+
+/* cv2.TERM_CRITERIA_* and cv2.OPTFLOW_* values (same numbers as OpenCV) */
+#define KLT_TERM_COUNT 1
+#define KLT_TERM_EPS 2
+#define KLT_OPTFLOW_USE_INITIAL_FLOW 4
+#define KLT_OPTFLOW_LK_GET_MIN_EIGENVALS 8
+
+typedef int klt_status;
+#define KLT_OK 0
+#define KLT_ERR_INVALID_ARG (-1)   /* cv2 would raise error -215 (assertion) */
+#define KLT_ERR_UNSUPPORTED (-2)   /* valid for cv2, outside this library's limits */
+#define KLT_ERR_NO_DEVICE (-3)     /* no CUDA device / wrong architecture: never falls back */
+#define KLT_ERR_OUT_OF_MEMORY (-4)
+#define KLT_ERR_INTERNAL (-5)
+
+typedef struct klt_ctx klt_ctx; /* opaque: device id, stream, workspaces, pinned staging */
+
+/* One pyramid level as the kernels see it (row `y` of batch item `b` starts at
+ * data + b*batch_stride + y*pitch). */
+typedef struct klt_level {
+    int32_t w, h;
+    int64_t pitch;        /* bytes between rows */
+    int64_t batch_stride; /* bytes between batch items */
+    int64_t offset;       /* byte offset of this level inside the pyramid buffer (levels >= 1) */
+} klt_level;
+
+/* Geometry of a pyramid: level 0 is the caller's image batch (never copied), levels 1..top live
+ * in ONE caller-provided buffer of `bytes` bytes.  Mirrors what cv2.buildOpticalFlowPyramid
+ * returns (retval = top, list of levels) -- SURVEY.md s8b / A.2. */
+typedef struct klt_pyr_layout {
+    int32_t top;    /* index of the last level built (cv2's retval; may be < max_level) */
+    int32_t batch;
+    klt_level level[KLT_MAX_LEVELS]; /* level[0].pitch/batch_stride are filled by the caller */
+    int64_t bytes;  /* size of the levels>=1 buffer for the whole batch */
+} klt_pyr_layout;
+
+/* ---- context -------------------------------------------------------------------------------- */
+klt_status klt_create(int device, klt_ctx** out);
+klt_status klt_destroy(klt_ctx* ctx);
+int klt_version(void);
+const char* klt_status_string(klt_status s);
+/* number of SMs / name of the device the context is bound to (for bench & grid sizing) */
+klt_status klt_device_info(klt_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ---- pinned host memory (so numpy inputs can be DMA'd without a staging copy) ---------------- */
+klt_status klt_host_alloc(void** ptr, int64_t bytes);
+klt_status klt_host_free(void* ptr);
+
+/* ---- pyramid (replaces cv2.buildOpticalFlowPyramid / pyrDown) ----------------- */
+/* Fills `out` for a w x h image batch: number of levels per cv2's rule (stop before a level whose
+ * width <= win_w or height <= win_h), per-level size / pitch / offset.  Host-only, no CUDA call. */
+klt_status klt_pyr_plan(int w, int h, int win_w, int win_h, int max_level, int batch, klt_pyr_layout* out);
+
+/* Builds levels 1..top of `batch` images.  d_img: level 0 (u8, pitch/batch_stride from
+ * layout->level[0]); d_pyr: buffer of layout->bytes.  One kernel launch per level. */
+klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* layout,
+                         uint8_t* d_pyr, void* stream);
+
+/* Single pyrDown step (cv2.pyrDown on 1-channel u8, BORDER_REFLECT_101), device pointers. */
+klt_status klt_pyr_down(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch,
+                        int64_t src_batch_stride, uint8_t* d_dst, int64_t dst_pitch,
+                        int64_t dst_batch_stride, int batch, void* stream);
+
+/* ---- Lucas-Kanade (replaces the per-level Scharr + LKTrackerInvoker loop) -- */
+typedef struct klt_lk_params {
+    int32_t win_w, win_h;
+    int32_t crit_type;      /* KLT_TERM_COUNT | KLT_TERM_EPS, as in cv2's criteria[0] */
+    int32_t crit_max_count; /* criteria[1] */
+    double crit_eps;        /* criteria[2] */
+    int32_t flags;          /* KLT_OPTFLOW_* */
+    double min_eig_threshold; /* cv2 default 1e-4 */
+} klt_lk_params;
+
+/* Tracks n_per_pair points in each of layout->batch frame pairs, all pyramid levels in ONE launch.
+ * d_prev_pts / d_next_pts: float2 [batch][n_per_pair]; d_status: u8; d_err: float;
+ * d_iters (optional, may be NULL): int32 LK iterations executed per point over all levels.
+ * d_next_pts is read only with KLT_OPTFLOW_USE_INITIAL_FLOW.  Points whose err cv2 leaves
+ * uninitialised get err = 0. */
+klt_status klt_lk_track(klt_ctx* ctx,
+                        const uint8_t* d_prev_img, const uint8_t* d_prev_pyr,
+                        const uint8_t* d_next_img, const uint8_t* d_next_pyr,
+                        const klt_pyr_layout* layout,
+                        const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                        int32_t* d_iters, int n_per_pair, const klt_lk_params* params, void* stream);
+
+/* ---- host-pointer entry points: exactly what a binding of the cv2 functions needs ------------ */
+/* cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, winSize, maxLevel, criteria[, flags,
+ * minEigThreshold]) -> nextPts, status, err.  HOST buffers (pinned or pageable); images u8 with
+ * arbitrary row pitch; points float32 [n][2].  Synchronous.  top_level_out (optional) receives the
+ * last pyramid level used. */
+klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx,
+                        const uint8_t* prev_img, int64_t prev_pitch,
+                        const uint8_t* next_img, int64_t next_pitch, int w, int h,
+                        const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n,
+                        int max_level, const klt_lk_params* params, int* top_level_out);
+
+/* cv2.buildOpticalFlowPyramid(img, winSize, maxLevel) without derivatives / borders: writes level
+ * l (l = 0..top) tightly packed (pitch = level width) at out + level_offsets[l].  Pass out = NULL
+ * to query `top` and the offsets / total size only. */
+klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                        int win_w, int win_h, int max_level, uint8_t* out, int64_t* level_offsets /*[KLT_MAX_LEVELS+1]*/,
+                        int* top_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLT_B200_H */

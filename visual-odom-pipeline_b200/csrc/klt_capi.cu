@@ -1,0 +1,365 @@
+// C ABI of libklt_b200.so (see include/klt_b200.h): context, pyramid planning, kernel launches
+// and the host-pointer entry points that stand in for cv2.calcOpticalFlowPyrLK /
+// cv2.buildOpticalFlowPyramid as called from reference src/extractor/extractor.py:44,45,65,66.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "klt_common.cuh"
+
+using namespace klt;
+
+struct klt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;  // for the *_host entry points
+    // device workspace of the *_host entry points (grown on demand, never shrunk)
+    uint8_t* d_ws = nullptr;
+    size_t d_ws_bytes = 0;
+    // pinned staging for results (and for pageable inputs)
+    uint8_t* h_ws = nullptr;
+    size_t h_ws_bytes = 0;
+};
+
+namespace {
+
+#define KLT_CUDA(expr)                                   \
+    do {                                                 \
+        cudaError_t e__ = (expr);                        \
+        if (e__ != cudaSuccess) return (klt_status)e__;  \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->d_ws_bytes) return KLT_OK;
+    if (ctx->d_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_ws); ctx->d_ws = nullptr; ctx->d_ws_bytes = 0; }
+    bytes = align_up(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    ctx->d_ws_bytes = bytes;
+    return KLT_OK;
+}
+
+klt_status ensure_host_ws(klt_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_ws_bytes) return KLT_OK;
+    if (ctx->h_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_ws); ctx->h_ws = nullptr; ctx->h_ws_bytes = 0; }
+    bytes = align_up(bytes + bytes / 4, 1 << 16);
+    cudaError_t e = cudaMallocHost(&ctx->h_ws, bytes);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    ctx->h_ws_bytes = bytes;
+    return KLT_OK;
+}
+
+void make_view(const klt_pyr_layout* lay, const uint8_t* img, const uint8_t* pyr, PyrView& v)
+{
+    v.top = lay->top;
+    for (int l = 0; l <= lay->top; ++l) {
+        const klt_level& s = lay->level[l];
+        v.lv[l].data = (l == 0) ? img : pyr + s.offset;
+        v.lv[l].batch_stride = s.batch_stride;
+        v.lv[l].pitch = (int)s.pitch;
+        v.lv[l].w = s.w;
+        v.lv[l].h = s.h;
+    }
+}
+
+klt_status check_layout(const klt_pyr_layout* lay)
+{
+    if (!lay || lay->top < 0 || lay->top >= KLT_MAX_LEVELS || lay->batch <= 0) return KLT_ERR_INVALID_ARG;
+    for (int l = 0; l <= lay->top; ++l) {
+        const klt_level& s = lay->level[l];
+        if (s.w <= 0 || s.h <= 0 || s.pitch < s.w || s.pitch > 0x7fffffffLL) return KLT_ERR_INVALID_ARG;
+        if (lay->batch > 1 && s.batch_stride < s.pitch * (int64_t)(s.h - 1) + s.w) return KLT_ERR_INVALID_ARG;
+    }
+    return KLT_OK;
+}
+
+// A.2 criteria normalisation (same clamps as OpenCV)
+void normalise_criteria(const klt_lk_params* p, int& max_count, double& eps2)
+{
+    double eps;
+    if ((p->crit_type & KLT_TERM_COUNT) == 0) max_count = 30;
+    else max_count = p->crit_max_count < 0 ? 0 : (p->crit_max_count > 100 ? 100 : p->crit_max_count);
+    if ((p->crit_type & KLT_TERM_EPS) == 0) eps = 0.01;
+    else eps = p->crit_eps < 0. ? 0. : (p->crit_eps > 10. ? 10. : p->crit_eps);
+    eps2 = eps * eps;
+}
+
+}  // namespace
+
+extern "C" {
+
+int klt_version(void) { return KLT_B200_VERSION; }
+
+const char* klt_status_string(klt_status s)
+{
+    switch (s) {
+        case KLT_OK: return "ok";
+        case KLT_ERR_INVALID_ARG: return "invalid argument (cv2 would raise an assertion error)";
+        case KLT_ERR_UNSUPPORTED: return "valid for OpenCV but outside libklt_b200 limits";
+        case KLT_ERR_NO_DEVICE: return "no sm_100 CUDA device available (there is no CPU fallback)";
+        case KLT_ERR_OUT_OF_MEMORY: return "out of memory";
+        case KLT_ERR_INTERNAL: return "internal error";
+        default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+    }
+}
+
+klt_status klt_create(int device, klt_ctx** out)
+{
+    if (!out) return KLT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return KLT_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    KLT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return KLT_ERR_NO_DEVICE;  // the fatbin holds sm_100a SASS only
+    KLT_CUDA(cudaSetDevice(device));
+    klt_ctx* ctx = new (std::nothrow) klt_ctx();
+    if (!ctx) return KLT_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    std::snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return (klt_status)e; }
+    klt_status s = lk_init(device);
+    if (s != KLT_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return s; }
+    *out = ctx;
+    return KLT_OK;
+}
+
+klt_status klt_destroy(klt_ctx* ctx)
+{
+    if (!ctx) return KLT_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->d_ws) cudaFree(ctx->d_ws);
+    if (ctx->h_ws) cudaFreeHost(ctx->h_ws);
+    delete ctx;
+    return KLT_OK;
+}
+
+klt_status klt_device_info(klt_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len)
+{
+    if (!ctx) return KLT_ERR_INVALID_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (name && name_len > 0) std::snprintf(name, (size_t)name_len, "%s", ctx->name);
+    return KLT_OK;
+}
+
+klt_status klt_host_alloc(void** ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return KLT_ERR_INVALID_ARG;
+    cudaError_t e = cudaMallocHost(ptr, (size_t)bytes);
+    if (e != cudaSuccess) { *ptr = nullptr; return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e; }
+    return KLT_OK;
+}
+
+klt_status klt_host_free(void* ptr)
+{
+    if (!ptr) return KLT_OK;
+    KLT_CUDA(cudaFreeHost(ptr));
+    return KLT_OK;
+}
+
+klt_status klt_pyr_plan(int w, int h, int win_w, int win_h, int max_level, int batch, klt_pyr_layout* out)
+{
+    if (!out || w <= 0 || h <= 0 || win_w <= 2 || win_h <= 2 || max_level < 0 || batch <= 0) return KLT_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    out->batch = batch;
+    out->level[0].w = w;
+    out->level[0].h = h;
+    out->level[0].pitch = w;                       // caller overrides with the real image pitch
+    out->level[0].batch_stride = (int64_t)w * h;   // idem
+    int top = 0;
+    int64_t off = 0;
+    int lw = w, lh = h;
+    while (top < max_level && top + 1 < KLT_MAX_LEVELS) {
+        const int nw = (lw + 1) / 2, nh = (lh + 1) / 2;
+        if (nw <= win_w || nh <= win_h) break;
+        ++top;
+        klt_level& L = out->level[top];
+        L.w = nw; L.h = nh;
+        L.pitch = (int64_t)align_up((size_t)nw, 32);
+        L.batch_stride = (int64_t)align_up((size_t)(L.pitch * nh), 256);
+        L.offset = off;
+        off += L.batch_stride * batch;
+        lw = nw; lh = nh;
+    }
+    out->top = top;
+    out->bytes = off;
+    return KLT_OK;
+}
+
+klt_status klt_pyr_down(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_batch_stride,
+                        uint8_t* d_dst, int64_t dst_pitch, int64_t dst_batch_stride, int batch, void* stream)
+{
+    if (!ctx) return KLT_ERR_INVALID_ARG;
+    return pyr_down_launch(d_src, w, h, src_pitch, src_batch_stride, d_dst, dst_pitch, dst_batch_stride, batch,
+                           ctx->sm_count, (cudaStream_t)stream);
+}
+
+klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* layout, uint8_t* d_pyr, void* stream)
+{
+    if (!ctx || !d_img) return KLT_ERR_INVALID_ARG;
+    klt_status s = check_layout(layout);
+    if (s != KLT_OK) return s;
+    if (layout->top > 0 && !d_pyr) return KLT_ERR_INVALID_ARG;
+    for (int l = 0; l < layout->top; ++l) {
+        const klt_level& a = layout->level[l];
+        const klt_level& b = layout->level[l + 1];
+        if (b.w != (a.w + 1) / 2 || b.h != (a.h + 1) / 2) return KLT_ERR_INVALID_ARG;
+        const uint8_t* src = (l == 0) ? d_img : d_pyr + a.offset;
+        s = pyr_down_launch(src, a.w, a.h, a.pitch, a.batch_stride, d_pyr + b.offset, b.pitch, b.batch_stride,
+                            layout->batch, ctx->sm_count, (cudaStream_t)stream);
+        if (s != KLT_OK) return s;
+    }
+    return KLT_OK;
+}
+
+klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* d_prev_pyr,
+                        const uint8_t* d_next_img, const uint8_t* d_next_pyr, const klt_pyr_layout* layout,
+                        const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                        int32_t* d_iters, int n_per_pair, const klt_lk_params* params, void* stream)
+{
+    if (!ctx || !params || !d_prev_img || !d_next_img || n_per_pair < 0) return KLT_ERR_INVALID_ARG;
+    klt_status s = check_layout(layout);
+    if (s != KLT_OK) return s;
+    if (layout->top > 0 && (!d_prev_pyr || !d_next_pyr)) return KLT_ERR_INVALID_ARG;
+    if (params->win_w <= 2 || params->win_h <= 2) return KLT_ERR_INVALID_ARG;
+    if (n_per_pair == 0) return KLT_OK;
+    if (!d_prev_pts || !d_next_pts || !d_status || !d_err) return KLT_ERR_INVALID_ARG;
+    LKLaunch L;
+    make_view(layout, d_prev_img, d_prev_pyr, L.prev);
+    make_view(layout, d_next_img, d_next_pyr, L.next);
+    L.prev_pts = d_prev_pts; L.next_pts = d_next_pts; L.status = d_status; L.err = d_err; L.iters = d_iters;
+    L.n_per_pair = n_per_pair;
+    L.batch = layout->batch;
+    L.win_w = params->win_w; L.win_h = params->win_h;
+    normalise_criteria(params, L.max_count, L.eps2);
+    L.flags = params->flags;
+    L.min_eig_thr = (float)params->min_eig_threshold;
+    return lk_launch(L, ctx->sm_count, (cudaStream_t)stream);
+}
+
+klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
+                                             const uint8_t* next_img, int64_t next_pitch, int w, int h,
+                                             const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                                             int n, int max_level, const klt_lk_params* params, int* top_level_out)
+{
+    if (!ctx || !params || !prev_img || !next_img || w <= 0 || h <= 0 || n < 0 || max_level < 0) return KLT_ERR_INVALID_ARG;
+    if (prev_pitch < w || next_pitch < w) return KLT_ERR_INVALID_ARG;
+    if (n > 0 && (!prev_pts || !next_pts || !status || !err)) return KLT_ERR_INVALID_ARG;
+    KLT_CUDA(cudaSetDevice(ctx->device));
+    // both images form a batch of 2 so that every pyramid level is ONE launch for the pair
+    klt_pyr_layout lay;
+    klt_status s = klt_pyr_plan(w, h, params->win_w, params->win_h, max_level, 2, &lay);
+    if (s != KLT_OK) return s;
+    if (top_level_out) *top_level_out = lay.top;
+    if (n == 0) return KLT_OK;
+    const size_t ipitch = align_up((size_t)w, 128);
+    const size_t ibytes = align_up(ipitch * (size_t)h, 256);
+    lay.level[0].pitch = (int64_t)ipitch;
+    lay.level[0].batch_stride = (int64_t)ibytes;
+    const size_t off_img = 0;
+    const size_t off_pyr = off_img + 2 * ibytes;
+    const size_t off_pts = off_pyr + align_up((size_t)lay.bytes, 256);
+    const size_t pts_bytes = align_up((size_t)n * 8, 256);
+    const size_t off_out = off_pts + pts_bytes;                 // nextPts | err | status, one D2H copy
+    const size_t out_bytes = (size_t)n * 8 + (size_t)n * 4 + (size_t)n;
+    s = ensure_device_ws(ctx, off_out + align_up(out_bytes, 256));
+    if (s != KLT_OK) return s;
+    s = ensure_host_ws(ctx, align_up(out_bytes, 256));
+    if (s != KLT_OK) return s;
+    uint8_t* d = ctx->d_ws;
+    cudaStream_t st = ctx->stream;
+    KLT_CUDA(cudaMemcpy2DAsync(d + off_img, ipitch, prev_img, (size_t)prev_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+    KLT_CUDA(cudaMemcpy2DAsync(d + off_img + ibytes, ipitch, next_img, (size_t)next_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+    float* d_next = reinterpret_cast<float*>(d + off_out);
+    float* d_err = reinterpret_cast<float*>(d + off_out + (size_t)n * 8);
+    uint8_t* d_status = d + off_out + (size_t)n * 12;
+    KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)
+        KLT_CUDA(cudaMemcpyAsync(d_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, st);
+    if (s != KLT_OK) return s;
+    // LK sees the two images as two single-image pyramids (batch 1) that share one buffer
+    klt_pyr_layout one = lay;
+    one.batch = 1;
+    const uint8_t* prev_pyr = d + off_pyr;
+    const uint8_t* next_pyr = d + off_pyr;  // next image = batch item 1: shift every level by its batch stride
+    PyrView pv, nv;
+    make_view(&one, d + off_img, prev_pyr, pv);
+    make_view(&one, d + off_img + ibytes, next_pyr, nv);
+    for (int l = 1; l <= lay.top; ++l) nv.lv[l].data += lay.level[l].batch_stride;
+    LKLaunch L;
+    L.prev = pv; L.next = nv;
+    L.prev_pts = reinterpret_cast<const float*>(d + off_pts);
+    L.next_pts = d_next; L.status = d_status; L.err = d_err; L.iters = nullptr;
+    L.n_per_pair = n; L.batch = 1;
+    L.win_w = params->win_w; L.win_h = params->win_h;
+    normalise_criteria(params, L.max_count, L.eps2);
+    L.flags = params->flags;
+    L.min_eig_thr = (float)params->min_eig_threshold;
+    s = lk_launch(L, ctx->sm_count, st);
+    if (s != KLT_OK) return s;
+    KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d + off_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    KLT_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(next_pts, ctx->h_ws, (size_t)n * 8);
+    std::memcpy(err, ctx->h_ws + (size_t)n * 8, (size_t)n * 4);
+    std::memcpy(status, ctx->h_ws + (size_t)n * 12, (size_t)n);
+    return KLT_OK;
+}
+
+klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                                               int win_w, int win_h, int max_level, uint8_t* out,
+                                               int64_t* level_offsets, int* top_out)
+{
+    if (!ctx || w <= 0 || h <= 0 || max_level < 0) return KLT_ERR_INVALID_ARG;
+    klt_pyr_layout lay;
+    klt_status s = klt_pyr_plan(w, h, win_w, win_h, max_level, 1, &lay);
+    if (s != KLT_OK) return s;
+    if (top_out) *top_out = lay.top;
+    int64_t off = 0;
+    for (int l = 0; l <= lay.top; ++l) {
+        if (level_offsets) level_offsets[l] = off;
+        off += (int64_t)lay.level[l].w * lay.level[l].h;
+    }
+    if (level_offsets) level_offsets[lay.top + 1] = off;
+    if (!out) return KLT_OK;
+    if (!img || pitch < w) return KLT_ERR_INVALID_ARG;
+    KLT_CUDA(cudaSetDevice(ctx->device));
+    const size_t ipitch = align_up((size_t)w, 128);
+    const size_t ibytes = align_up(ipitch * (size_t)h, 256);
+    lay.level[0].pitch = (int64_t)ipitch;
+    lay.level[0].batch_stride = (int64_t)ibytes;
+    s = ensure_device_ws(ctx, ibytes + (size_t)lay.bytes);
+    if (s != KLT_OK) return s;
+    uint8_t* d = ctx->d_ws;
+    cudaStream_t st = ctx->stream;
+    KLT_CUDA(cudaMemcpy2DAsync(d, ipitch, img, (size_t)pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+    s = klt_pyr_build(ctx, d, &lay, d + ibytes, st);
+    if (s != KLT_OK) return s;
+    int64_t o = 0;
+    for (int l = 0; l <= lay.top; ++l) {
+        const klt_level& L = lay.level[l];
+        const uint8_t* src = (l == 0) ? d : d + ibytes + L.offset;
+        KLT_CUDA(cudaMemcpy2DAsync(out + o, (size_t)L.w, src, (size_t)L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost, st));
+        o += (int64_t)L.w * L.h;
+    }
+    KLT_CUDA(cudaStreamSynchronize(st));
+    return KLT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Shared device/host helpers for the KLT kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "klt_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libklt_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace klt {
+
+// One pyramid level as kernel argument (device pointer already offset to batch item 0).
+struct LevelView {
+    const uint8_t* data;
+    long long batch_stride;
+    int pitch;
+    int w, h;
+};
+
+struct PyrView {
+    LevelView lv[KLT_MAX_LEVELS];
+    int top;
+};
+
+// BORDER_REFLECT_101 for any distance.  len >= 1.
+__host__ __device__ __forceinline__ int reflect101(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        p = (p < 0) ? -p : 2 * len - 2 - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// u / d for small operands via a 12.20 reciprocal: exact for u < 4096, 1 <= d <= 64
+// (u*magic < 2^32 and the rounding excess u*e/2^20 stays below 1/d).
+__host__ __device__ __forceinline__ unsigned fastdiv_magic(unsigned d) { return ((1u << 20) + d - 1u) / d; }
+__host__ __device__ __forceinline__ unsigned fastdiv(unsigned u, unsigned magic) { return (u * magic) >> 20; }
+
+klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, long long sbatch,
+                           uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
+                           cudaStream_t stream);
+
+struct LKLaunch {
+    PyrView prev, next;
+    const float* prev_pts;
+    float* next_pts;
+    uint8_t* status;
+    float* err;
+    int* iters;
+    int n_per_pair;
+    int batch;
+    int win_w, win_h;
+    int max_count;
+    double eps2;
+    int flags;
+    float min_eig_thr;
+};
+
+klt_status lk_launch(const LKLaunch& L, int sm_count, cudaStream_t stream);
+klt_status lk_init(int device);
+
+}  // namespace klt

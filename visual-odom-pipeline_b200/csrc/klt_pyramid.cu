@@ -1,0 +1,226 @@
+// K1: batched 5-tap separable pyrDown for u8 images on sm_100a.
+//
+// Replaces cv2.pyrDown as run inside cv2.buildOpticalFlowPyramid / calcOpticalFlowPyrLK, which the
+// reference reaches from src/extractor/extractor.py:44,45,65,66.  Arithmetic:
+//   dst(x,y) = ( sum_{i,j in [-2,2]} k_i k_j src(R(2x+i), R(2y+j)) + 128 ) >> 8,  k = [1 4 6 4 1],
+//   R = BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2).  Integer, bit-exact.
+//
+// Design (HBM-bound byte work, no tensor cores):
+//  * one warp owns a strip of 64*NOUT input columns x (2R+3) input rows and produces 32*NOUT x R
+//    outputs; each lane loads its own 2*NOUT contiguous bytes per input row with ONE 64/128-bit
+//    coalesced load and gets the 2+1 halo columns from its neighbours by warp shuffle (register
+//    halo staging -- no shared-memory round trip, every input byte crosses the LSU once);
+//  * bytes are widened to packed u16x2 lanes (PRMT) so one 32-bit op filters two columns; the
+//    vertical pass is a sliding window (T_y = r[2y] + 4 r[2y+1] + r[2y+2]; V_y = T_{y-1} + T_y +
+//    4 r[2y]) so each input row is loaded and unpacked once per strip; the horizontal pass works
+//    on funnel-shifted packed pairs; max partial sum 255*256 = 65280 fits the 16-bit lanes;
+//  * next strip rows are prefetched into registers while the current output row is computed;
+//  * image borders (REFLECT_101) and unaligned pitches take a byte-gather path in the edge lanes
+//    only; interior lanes never branch on coordinates.
+#include "klt_common.cuh"
+
+namespace klt {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// (b0, 0, b2, 0) and (b1, 0, b3, 0) of a word: even / odd columns as packed u16x2
+__device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return prmt(w, 0u, 0x4240u); }
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return prmt(w, 0u, 0x4341u); }
+
+template <int NOUT>
+struct RawRow {
+    uint32_t w[NOUT / 2];  // own 2*NOUT bytes
+    uint32_t l, r;         // word left of / right of the own bytes (from neighbours)
+};
+
+// Load the raw bytes one lane needs from one (already row-reflected) input row.
+template <int NOUT, bool ALIGNED>
+__device__ __forceinline__ void load_row(const uint8_t* __restrict__ row, int cb, int w, bool fast,
+                                         int lane, RawRow<NOUT>& out)
+{
+    constexpr int NW = NOUT / 2;
+    if (ALIGNED && fast) {
+        if constexpr (NOUT == 8) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(row + cb));
+            out.w[0] = v.x; out.w[1] = v.y; out.w[2] = v.z; out.w[3] = v.w;
+        } else {
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(row + cb));
+            out.w[0] = v.x; out.w[1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v |= (uint32_t)__ldg(row + reflect101(cb + 4 * i + j, w)) << (8 * j);
+            out.w[i] = v;
+        }
+    }
+    out.l = __shfl_up_sync(0xffffffffu, out.w[NW - 1], 1);
+    out.r = __shfl_down_sync(0xffffffffu, out.w[0], 1);
+    if (lane == 0) {
+        out.l = ((uint32_t)__ldg(row + reflect101(cb - 2, w)) << 16) |
+                ((uint32_t)__ldg(row + reflect101(cb - 1, w)) << 24);
+    }
+    if (lane == 31) out.r = (uint32_t)__ldg(row + reflect101(cb + 2 * NOUT, w));
+}
+
+// packed u16x2 columns of one row: [0]=(cb-4,cb-2) [1]=(cb-3,cb-1) then per own word i:
+// [2+2i]=(cb+4i, cb+4i+2) [3+2i]=(cb+4i+1, cb+4i+3), last = (cb+2NOUT, junk)
+template <int NOUT>
+__device__ __forceinline__ void unpack_row(const RawRow<NOUT>& raw, uint32_t (&p)[NOUT + 3])
+{
+    constexpr int NW = NOUT / 2;
+    p[0] = even_bytes(raw.l);
+    p[1] = odd_bytes(raw.l);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        p[2 + 2 * i] = even_bytes(raw.w[i]);
+        p[3 + 2 * i] = odd_bytes(raw.w[i]);
+    }
+    p[NOUT + 2] = even_bytes(raw.r);
+}
+
+template <int NOUT, bool ALIGNED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
+                uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+{
+    constexpr int NW = NOUT / 2;
+    constexpr int NP = NOUT + 3;
+    const int lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (task >= n_tasks) return;  // warp-uniform
+
+    const int tx = (int)(task % tiles_x);
+    const long long t2 = task / tiles_x;
+    const int sy = (int)(t2 % strips_y);
+    const int b = (int)(t2 / strips_y);
+
+    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
+    uint8_t* __restrict__ dimg = dst + (long long)b * dbatch;
+
+    const int cb = tx * (64 * NOUT) + 2 * NOUT * lane;  // first own input column
+    const bool fast = (cb + 2 * NOUT <= w);             // all own columns inside the image
+    const int y0 = sy * rows_per_strip;
+    const int y1 = min(y0 + rows_per_strip, dh);
+
+    uint32_t tprev[NP], rc[NP];
+    {
+        RawRow<NOUT> a, bq, c;
+        load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y0 - 2, h) * spitch, cb, w, fast, lane, a);
+        load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y0 - 1, h) * spitch, cb, w, fast, lane, bq);
+        load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y0, h) * spitch, cb, w, fast, lane, c);
+        uint32_t pa[NP], pb[NP];
+        unpack_row<NOUT>(a, pa);
+        unpack_row<NOUT>(bq, pb);
+        unpack_row<NOUT>(c, rc);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) tprev[i] = pa[i] + 4u * pb[i] + rc[i];
+    }
+
+    RawRow<NOUT> nxt_o, nxt_e;  // prefetched rows 2y+1, 2y+2
+    load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y0 + 1, h) * spitch, cb, w, fast, lane, nxt_o);
+    load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y0 + 2, h) * spitch, cb, w, fast, lane, nxt_e);
+
+    const int xo = cb >> 1;  // first output column of this lane
+    for (int y = y0; y < y1; ++y) {
+        uint32_t ro[NP], re[NP];
+        unpack_row<NOUT>(nxt_o, ro);
+        unpack_row<NOUT>(nxt_e, re);
+        if (y + 1 < y1) {  // warp-uniform: prefetch the next output row's inputs
+            load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y + 3, h) * spitch, cb, w, fast, lane, nxt_o);
+            load_row<NOUT, ALIGNED>(simg + (long long)reflect101(2 * y + 4, h) * spitch, cb, w, fast, lane, nxt_e);
+        }
+        uint32_t v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            uint32_t t = rc[i] + 4u * ro[i] + re[i];
+            v[i] = tprev[i] + t + 4u * rc[i];
+            tprev[i] = t;
+            rc[i] = re[i];
+        }
+        // horizontal pass: own word i gives outputs 2i (centre col cb+4i) and 2i+1 (cb+4i+2)
+        uint32_t s[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t e_m = v[2 * i], o_m = v[2 * i + 1];      // (c-4,c-2) (c-3,c-1)
+            const uint32_t e_c = v[2 * i + 2], o_c = v[2 * i + 3];  // (c,c+2)   (c+1,c+3)
+            const uint32_t e_p = v[2 * i + 4];                      // (c+4, .)
+            const uint32_t a = __funnelshift_r(e_m, e_c, 16);       // (c-2, c)
+            const uint32_t c = __funnelshift_r(e_c, e_p, 16);       // (c+2, c+4)
+            const uint32_t oa = __funnelshift_r(o_m, o_c, 16);      // (c-1, c+1)
+            s[i] = a + c + 6u * e_c + 4u * (oa + o_c) + 0x00800080u;  // +128 per lane; >>8 below
+        }
+        uint8_t* drow = dimg + (long long)y * dpitch + xo;
+        if (ALIGNED && xo + NOUT <= dw) {
+            if constexpr (NOUT == 8) {
+                uint2 o;
+                o.x = prmt(s[0], s[1], 0x7531u);
+                o.y = prmt(s[2], s[3], 0x7531u);
+                *reinterpret_cast<uint2*>(drow) = o;
+            } else {
+                *reinterpret_cast<uint32_t*>(drow) = prmt(s[0], s[1], 0x7531u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                if (xo + 2 * i < dw) drow[2 * i] = (uint8_t)(s[i] >> 8);
+                if (xo + 2 * i + 1 < dw) drow[2 * i + 1] = (uint8_t)(s[i] >> 24);
+            }
+        }
+    }
+}
+
+template <int NOUT, bool ALIGNED>
+klt_status launch_t(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                    int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count,
+                    cudaStream_t stream)
+{
+    const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
+    // strip height: tall strips amortise the 3 halo rows; shrink them until the grid can fill the chip
+    int rows = 16;
+    const long long want = (long long)sm_count * kWarpsPerBlock * 4;
+    while (rows > 2 && (long long)tiles_x * ((dh + rows - 1) / rows) * batch < want) rows >>= 1;
+    const int strips_y = (dh + rows - 1) / rows;
+    const long long n_tasks = (long long)tiles_x * strips_y * batch;
+    const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    pyr_down_kernel<NOUT, ALIGNED><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+}  // namespace
+
+klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, long long sbatch,
+                           uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
+                           cudaStream_t stream)
+{
+    if (!src || !dst || w <= 0 || h <= 0 || batch <= 0 || spitch < w) return KLT_ERR_INVALID_ARG;
+    const int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    if (dpitch < dw) return KLT_ERR_INVALID_ARG;
+    const bool aligned = (((uintptr_t)src | (uintptr_t)spitch | (uintptr_t)sbatch) % 16 == 0) &&
+                         (((uintptr_t)dst | (uintptr_t)dpitch | (uintptr_t)dbatch) % 8 == 0);
+    // 8 outputs per lane (128-bit loads) unless the 256-wide warp tile would waste > 1/4 of its lanes
+    const int t8 = (dw + 255) / 256 * 256, t4 = (dw + 127) / 128 * 128;
+    const bool use8 = (t8 * 3 <= dw * 4) || (t8 == t4);
+    if (aligned) {
+        return use8 ? launch_t<8, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
+                    : launch_t<4, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+    }
+    return launch_t<4, false>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+}
+
+}  // namespace klt
