@@ -1,0 +1,286 @@
+"""GPU tier (pytest -m gpu, B200): the CUDA path, called through the C ABI (ctypes), against the C
+oracle, the committed golden vectors and live cv2 on the same seeded inputs.
+
+Bars (BASELINE.json north_star): pyramid levels bit-exact; positions within 0.01 px; status identical
+on >= 99.9 % of points.  The kernels reproduce OpenCV's arithmetic exactly, so
+these tests assert the stronger bit-exact property and log every mismatching point."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import assert_lk_equal, load_golden
+from visual_odom_pipeline_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL_PX = 0.01        # north_star tolerance, stated here although the expected difference is 0
+STATUS_AGREE_MIN = 0.999
+
+
+def crit_of(g):
+    return (int(g["criteria"][0]), int(g["criteria"][1]), float(g["criteria"][2]))
+
+
+@pytest.fixture(scope="module")
+def cv2():
+    return pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    return torch
+
+
+def test_native_library_is_loaded_and_bound_to_b200(klt):
+    ctx = klt.default_context(0)
+    assert ctx.cc[0] == 10 and ctx.sm_count >= 100, (ctx.name, ctx.cc, ctx.sm_count)
+    with open("/proc/self/maps") as f:
+        assert "libklt_b200.so" in f.read()
+
+
+# ---------------------------------------------------------------- pyramid ------------------------
+@pytest.mark.parametrize("hw", [(376, 1241), (480, 640), (768, 1024), (135, 241), (47, 156), (33, 17), (50, 70), (2160, 3840)])
+def test_pyramid_bit_exact_vs_oracle(klt, oracle, hw):
+    h, w = hw
+    img = S.texture(h, w, seed=h * 3 + w).astype(np.uint8)
+    top, levels = klt.buildOpticalFlowPyramid(img, (5, 5), 8)
+    otop, olevels = oracle.build_pyramid(img, (5, 5), 8)
+    assert top == otop and len(levels) == len(olevels)
+    for l, (a, b) in enumerate(zip(levels, olevels)):
+        assert a.shape == b.shape and np.array_equal(a, b), "level %d of %s" % (l, hw)
+
+
+def test_pyramid_matches_golden_and_cv2(klt, cv2):
+    g = load_golden("pyramid")
+    top, levels = klt.buildOpticalFlowPyramid(g["img"], (21, 21), 8)
+    assert top == int(g["top_win21_max8"])
+    top, levels = klt.buildOpticalFlowPyramid(g["img"], (3, 3), 4)
+    for l, k in enumerate(("l1", "l2", "l3", "l4"), 1):
+        assert np.array_equal(levels[l], g[k]), k
+    ctop, clevels = cv2.buildOpticalFlowPyramid(g["img"], (21, 21), 8, None, False)
+    ktop, klevels = klt.buildOpticalFlowPyramid(g["img"], (21, 21), 8)
+    assert ctop == ktop and all(np.array_equal(a, b) for a, b in zip(klevels, clevels))
+
+
+def test_pyramid_noncontiguous_and_constant_inputs(klt, oracle):
+    big = S.texture(200, 300, seed=5).astype(np.uint8)
+    view = big[3:190:1, 7:250]                      # row-strided view, like a cv2 ROI
+    assert not view.flags["C_CONTIGUOUS"]
+    _, lv = klt.buildOpticalFlowPyramid(view, (5, 5), 3)
+    _, ol = oracle.build_pyramid(np.ascontiguousarray(view), (5, 5), 3)
+    assert all(np.array_equal(a, b) for a, b in zip(lv, ol))
+    for val in (0, 255):                            # saturation: 255 * 256 sums must not wrap
+        _, lv = klt.buildOpticalFlowPyramid(np.full((64, 96), val, np.uint8), (5, 5), 2)
+        assert all((x == val).all() for x in lv)
+
+
+def test_device_pyramid_batched_aligned_and_unaligned(klt, oracle, torch_cuda):
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    B, H, W = 5, 94, 311
+    imgs = np.stack([S.texture(H, W, seed=40 + i).astype(np.uint8) for i in range(B)])
+    for aligned in (True, False):
+        if aligned:
+            d = T.alloc_image_batch(B, H, W)
+            d.copy_(torch.from_numpy(imgs))
+        else:
+            d = torch.from_numpy(imgs).cuda()      # W = 311: rows are not 16-byte aligned -> byte path
+        pyr = T.DevicePyramid(d, (5, 5), 4)
+        torch.cuda.synchronize()
+        for b in range(B):
+            _, ol = oracle.build_pyramid(imgs[b], (5, 5), 4)
+            for l in range(pyr.top + 1):
+                assert np.array_equal(pyr.level(l)[b].cpu().numpy(), ol[l]), (aligned, b, l)
+
+
+# ---------------------------------------------------------------- LK -----------------------------
+@pytest.mark.parametrize("name", ["lk_default", "lk_reference", "lk_hard", "lk_count_only", "lk_eps_only", "lk_mineig_flag", "lk_level0"])
+def test_lk_matches_golden(klt, name):
+    g = load_golden(name)
+    got = klt.calcOpticalFlowPyrLK(g["prev"], g["next"], g["prevPts"], None, winSize=tuple(int(v) for v in g["winSize"]),
+                                   maxLevel=int(g["maxLevel"]), criteria=crit_of(g), flags=int(g["flags"]))
+    assert got[0].shape == g["nextPts"].shape and got[1].shape == g["status"].shape and got[2].shape == g["err"].shape
+    assert got[0].dtype == np.float32 and got[1].dtype == np.uint8 and got[2].dtype == np.float32
+    assert_lk_equal(got, (g["nextPts"], g["status"], g["err"]), name)
+
+
+CONFIGS = [
+    # id, h, w, n, win, maxLevel, criteria, motion, margin, extra   (BASELINE.json configs at oracle-friendly N)
+    ("parking", 480, 640, 500, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 0, {}),
+    ("kitti", 376, 1241, 2000, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 0, {}),
+    ("kitti_ref_params", 376, 1241, 2000, (31, 31), 3, (3, 30, 0.03), S.BENIGN, 0, {}),
+    ("kitti_hard", 376, 1241, 2000, (21, 21), 3, (3, 30, 0.01), S.HARD, 60, dict(noise_sigma=3.0, flat_cols=(400, 700))),
+    ("kitti_hard31", 376, 1241, 2000, (31, 31), 3, (3, 30, 0.03), S.HARD, 60, dict(noise_sigma=3.0, flat_cols=(400, 700))),
+    ("malaga", 768, 1024, 3000, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 0, {}),
+    ("nonsquare", 240, 320, 400, (20, 12), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("tall_win", 240, 320, 400, (13, 29), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("win3", 240, 320, 400, (3, 3), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("win8", 240, 320, 400, (8, 8), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("win40", 240, 320, 400, (40, 40), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("win64", 240, 320, 200, (64, 64), 3, (3, 30, 0.01), S.HARD, 30, {}),
+    ("truncated_pyr", 376, 1241, 500, (21, 21), 8, (3, 30, 0.01), S.BENIGN, 30, {}),
+    ("level0_only", 376, 1241, 500, (21, 21), 0, (3, 30, 0.01), S.BENIGN, 30, {}),
+    ("count_only", 240, 320, 400, (21, 21), 3, (1, 10, 0.01), S.BENIGN, 30, {}),
+    ("eps_only", 240, 320, 400, (21, 21), 3, (2, 30, 0.05), S.BENIGN, 30, {}),
+    ("clamped_crit", 240, 320, 400, (21, 21), 3, (3, 200, 20.0), S.BENIGN, 30, {}),
+    ("zero_iters", 240, 320, 400, (21, 21), 3, (3, 0, 0.01), S.BENIGN, 30, {}),
+    ("tiny_image", 50, 70, 100, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 30, {}),
+]
+
+
+@pytest.mark.parametrize("case", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_lk_bit_exact_vs_oracle_and_cv2(klt, oracle, cv2, case):
+    _, h, w, n, win, lvl, crit, motion, margin, kw = case
+    a, b = S.frame_pair(h, w, seed=7, motion=motion, **kw)
+    p = S.uniform_points(n, h, w, seed=3, margin=margin)
+    got = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=crit)
+    want = oracle.calc_optical_flow_pyr_lk(a, b, p, None, win, lvl, crit)
+    ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=crit)
+    # the north-star gates first (tolerances stated), then the stronger bit-exact check
+    agree = (got[1] == ref[1]).mean()
+    assert agree >= STATUS_AGREE_MIN, "status agreement %.5f" % agree
+    both = ((got[1] == 1) & (ref[1] == 1)).ravel()
+    if both.any():
+        assert np.abs(got[0].reshape(-1, 2)[both] - ref[0].reshape(-1, 2)[both]).max() <= POS_TOL_PX
+    assert_lk_equal(got, want, "vs oracle")
+    assert_lk_equal(got, ref, "vs cv2")
+
+
+def test_lk_point_layouts_and_special_points(klt, cv2):
+    a, b = S.frame_pair(120, 160, seed=2)
+    base = S.uniform_points(40, 120, 160, seed=9)
+    for shape in [(40, 1, 2), (40, 2), (1, 40, 2)]:
+        p = base.reshape(shape)
+        got = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        assert got[0].shape == ref[0].shape == shape and got[1].shape == ref[1].shape and got[2].shape == ref[2].shape
+        assert_lk_equal(got, ref, str(shape))
+    p = np.array([[np.nan, 10], [1e9, 1e9], [-500, 20], [0, 0], [159.9, 119.9], [80, 60], [-10.5, -10.5], [np.inf, 3]], np.float32).reshape(-1, 1, 2)
+    got = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    assert np.array_equal(got[1], ref[1])
+    fin = np.isfinite(ref[0]).all(-1).ravel()
+    assert np.array_equal(got[0].reshape(-1, 2)[fin].view(np.uint32), ref[0].reshape(-1, 2)[fin].view(np.uint32))
+    assert np.array_equal(np.isnan(got[0]), np.isnan(ref[0]))
+    one = klt.calcOpticalFlowPyrLK(a, b, base[:1], None)
+    assert_lk_equal(one, cv2.calcOpticalFlowPyrLK(a, b, base[:1], None), "N=1")
+    assert klt.calcOpticalFlowPyrLK(a, b, base[:0], None) == (None, None, None)
+
+
+def test_lk_initial_flow_flag(klt, cv2):
+    a, b = S.frame_pair(120, 160, seed=4)
+    p = S.uniform_points(50, 120, 160, seed=1)
+    guess = (p + np.float32(2.0)).astype(np.float32)
+    ref = cv2.calcOpticalFlowPyrLK(a, b, p, guess.copy(), winSize=(21, 21), maxLevel=2, criteria=(3, 30, 0.01), flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    got = klt.calcOpticalFlowPyrLK(a, b, p, guess.copy(), winSize=(21, 21), maxLevel=2, criteria=(3, 30, 0.01), flags=klt.OPTFLOW_USE_INITIAL_FLOW)
+    assert_lk_equal(got, ref)
+
+
+def test_inputs_not_mutated_and_outputs_fresh(klt):
+    a, b = S.frame_pair(96, 128, seed=6)
+    p = S.uniform_points(30, 96, 128, seed=2)
+    a0, b0, p0 = a.copy(), b.copy(), p.copy()
+    r1 = klt.calcOpticalFlowPyrLK(a, b, p, None)
+    r2 = klt.calcOpticalFlowPyrLK(a, b, p, None)
+    assert np.array_equal(a, a0) and np.array_equal(b, b0) and np.array_equal(p, p0)
+    assert r1[0] is not r2[0] and np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1])
+
+
+def test_reference_call_pattern_extend_tracks(klt, cv2):
+    """The exact sequence of reference src/extractor/extractor.py:43-57 (forward call, second call from
+    the result, bidirectional distance, inclusive bounds filter) gives the same survivors."""
+    lk = dict(winSize=(31, 31), maxLevel=3, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.03))
+    im0, im1 = S.frame_pair(376, 1241, seed=12)
+    uv = S.uniform_points(600, 376, 1241, seed=8).reshape(-1, 2)
+    p0 = np.float32([u.reshape(2, 1).T for u in uv]).reshape(-1, 1, 2)
+
+    def run(fn):
+        p1, _st, _err = fn(im0, im1, p0, None, **lk)
+        p0r, _st, _err = fn(im0, im1, p1, None, **lk)
+        d = abs(p0 - p0r).reshape(-1, 2).max(-1)
+        good = d < np.inf
+        keep = [i for i, ((x, y), g) in enumerate(zip(p1.reshape(-1, 2), good)) if g and 0 <= x <= im1.shape[1] and 0 <= y <= im1.shape[0]]
+        return p1, p0r, keep
+    a, b = run(cv2.calcOpticalFlowPyrLK), run(klt.calcOpticalFlowPyrLK)
+    assert a[2] == b[2]
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+# ---------------------------------------------------------------- device / batch API -------------
+def test_batched_device_api_equals_per_pair_host_calls(klt, oracle, torch_cuda):
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    B, H, W, N = 6, 188, 621, 300
+    pairs = [S.frame_pair(H, W, seed=70 + i) for i in range(B)]
+    pts = np.stack([S.uniform_points(N, H, W, seed=i, margin=20).reshape(N, 2) for i in range(B)])
+    prev = T.alloc_image_batch(B, H, W); prev.copy_(torch.from_numpy(np.stack([p[0] for p in pairs])))
+    nxt = T.alloc_image_batch(B, H, W); nxt.copy_(torch.from_numpy(np.stack([p[1] for p in pairs])))
+    P0 = T.DevicePyramid(prev, (21, 21), 3)
+    P1 = T.DevicePyramid(nxt, (21, 21), 3)
+    q, st, er, it = T.lk_track(P0, P1, torch.from_numpy(pts).cuda(), criteria=(3, 30, 0.01), return_iters=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        want = oracle.calc_optical_flow_pyr_lk(pairs[b][0], pairs[b][1], pts[b], None, (21, 21), 3, (3, 30, 0.01), return_iters=True)
+        assert_lk_equal((q[b].cpu().numpy(), st[b].cpu().numpy(), er[b].cpu().numpy()), want[:3], "pair %d" % b)
+        assert np.array_equal(it[b].cpu().numpy(), want[3]), "iteration counts, pair %d" % b
+
+
+def test_torch_tensor_dropin_and_tracker_sequence(klt, cv2, torch_cuda):
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    frames = S.sequence(120, 160, 5, seed=31)
+    p = S.uniform_points(80, 120, 160, seed=4)
+    # drop-in with CUDA tensors
+    got = klt.calcOpticalFlowPyrLK(torch.from_numpy(frames[0]).cuda(), torch.from_numpy(frames[1]).cuda(), torch.from_numpy(p).cuda(), None,
+                                   winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+    ref = cv2.calcOpticalFlowPyrLK(frames[0], frames[1], p, None, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+    assert tuple(got[0].shape) == ref[0].shape
+    assert_lk_equal(tuple(t.cpu().numpy() for t in got), ref)
+    # tracker keeps the pyramid of the last frame: same results as pairwise cv2 calls
+    trk = T.KLTTracker(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03)).reset(torch.from_numpy(frames[0]).cuda())
+    cur = p.copy()
+    for t in range(1, len(frames)):
+        q, st, er, back = trk.track(torch.from_numpy(frames[t]).cuda(), torch.from_numpy(cur.reshape(1, -1, 2)).cuda(), bidirectional=True)
+        ref = cv2.calcOpticalFlowPyrLK(frames[t - 1], frames[t], cur, None, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+        refb = cv2.calcOpticalFlowPyrLK(frames[t - 1], frames[t], ref[0], None, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+        assert_lk_equal((q.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy()), ref, "frame %d" % t)
+        assert np.array_equal(back.cpu().numpy().reshape(-1, 2).view(np.uint32), refb[0].reshape(-1, 2).view(np.uint32))
+        cur = ref[0]
+
+
+# ---------------------------------------------------------------- full-size properties -----------
+def test_full_size_stress_config_vs_cv2_and_properties(klt, cv2):
+    """BASELINE configs[4]: 3840x2160, dense grid ~100k points, win 31, maxLevel 5 (too big for the scalar
+    oracle in seconds -> live cv2 is the checker, plus size-independent properties)."""
+    h, w = 2160, 3840
+    a, b = S.frame_pair(h, w, seed=7)
+    p = S.grid_points(422, 237, h, w)
+    assert p.shape[0] == 100014
+    got = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(31, 31), maxLevel=5, criteria=(3, 30, 0.01))
+    ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(31, 31), maxLevel=5, criteria=(3, 30, 0.01))
+    assert_lk_equal(got, ref, "4K")
+    again = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(31, 31), maxLevel=5, criteria=(3, 30, 0.01))
+    assert all(np.array_equal(x, y) for x, y in zip(got, again)), "not deterministic"
+    perm = np.random.default_rng(0).permutation(p.shape[0])          # per-point independence
+    shuf = klt.calcOpticalFlowPyrLK(a, b, p[perm], None, winSize=(31, 31), maxLevel=5, criteria=(3, 30, 0.01))
+    assert np.array_equal(shuf[0], got[0][perm]) and np.array_equal(shuf[1], got[1][perm])
+
+
+def test_integer_shift_is_recovered_at_kitti_size(klt):
+    """Property: next = prev shifted by whole pixels -> interior points move by exactly that shift
+    (to the eps of the criteria), independent of any reference implementation."""
+    h, w = 376, 1241
+    base = S.texture(h + 16, w + 16, seed=3).astype(np.uint8)
+    prev = np.ascontiguousarray(base[8:8 + h, 8:8 + w])
+    dx, dy = 5, -3
+    nxt = np.ascontiguousarray(base[8 - dy:8 - dy + h, 8 - dx:8 - dx + w])
+    p = S.uniform_points(2000, h - 80, w - 80, seed=1) + np.float32(40)
+    q, st, er = klt.calcOpticalFlowPyrLK(prev, nxt, p, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    ok = st.ravel() == 1
+    assert ok.mean() > 0.98
+    d = (q - p).reshape(-1, 2)[ok]
+    assert np.abs(d - np.array([dx, dy], np.float32)).max() < 0.05
+    assert (er.ravel()[ok] < 1.0).all()
