@@ -83,10 +83,11 @@ klt_status klt_host_free(void* ptr);
  * width <= win_w or height <= win_h), per-level size / pitch / offset.  Host-only, no CUDA call. */
 klt_status klt_pyr_plan(int w, int h, int win_w, int win_h, int max_level, int batch, klt_pyr_layout* out);
 
-/* Builds levels 1..top of `batch` images.  d_img: level 0 (u8, pitch/batch_stride from
- * layout->level[0]); d_pyr: buffer of layout->bytes.  One kernel launch per level. */
+/* Builds levels 1..top of batch items [first_item, first_item + n_items) (n_items <= 0: all of
+ * them).  d_img: level 0 of item 0 (u8, pitch/batch_stride from layout->level[0]); d_pyr: buffer of
+ * layout->bytes.  One kernel launch per level for the whole item range. */
 klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* layout,
-                         uint8_t* d_pyr, void* stream);
+                         uint8_t* d_pyr, int first_item, int n_items, void* stream);
 
 /* Single pyrDown step (cv2.pyrDown on 1-channel u8, BORDER_REFLECT_101), device pointers. */
 klt_status klt_pyr_down(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch,
@@ -103,15 +104,19 @@ typedef struct klt_lk_params {
     double min_eig_threshold; /* cv2 default 1e-4 */
 } klt_lk_params;
 
-/* Tracks n_per_pair points in each of layout->batch frame pairs, all pyramid levels in ONE launch.
- * d_prev_pts / d_next_pts: float2 [batch][n_per_pair]; d_status: u8; d_err: float;
+/* Tracks n_per_pair points in each of n_pairs frame pairs, all pyramid levels in ONE launch.
+ * `layout` describes both pyramid buffers (they may be the same buffer): pair i uses batch item
+ * prev_first + i*pair_stride of (d_prev_img, d_prev_pyr) and item next_first + i*pair_stride of
+ * (d_next_img, d_next_pyr), so one batched pyramid build can hold previous and next frames side by
+ * side (interleaved: prev_first 0, next_first 1, pair_stride 2; a frame ring: 0, 1, 1).
+ * d_prev_pts / d_next_pts: float2 [n_pairs][n_per_pair]; d_status: u8; d_err: float;
  * d_iters (optional, may be NULL): int32 LK iterations executed per point over all levels.
  * d_next_pts is read only with KLT_OPTFLOW_USE_INITIAL_FLOW.  Points whose err cv2 leaves
  * uninitialised get err = 0. */
 klt_status klt_lk_track(klt_ctx* ctx,
                         const uint8_t* d_prev_img, const uint8_t* d_prev_pyr,
                         const uint8_t* d_next_img, const uint8_t* d_next_pyr,
-                        const klt_pyr_layout* layout,
+                        const klt_pyr_layout* layout, int prev_first, int next_first, int pair_stride, int n_pairs,
                         const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
                         int32_t* d_iters, int n_per_pair, const klt_lk_params* params, void* stream);
 

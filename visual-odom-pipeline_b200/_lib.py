@@ -44,9 +44,9 @@ SYMBOLS = {
     "klt_host_alloc": (_c.c_int, [_c.POINTER(_P), _c.c_int64]),
     "klt_host_free": (_c.c_int, [_P]),
     "klt_pyr_plan": (_c.c_int, [_c.c_int] * 6 + [_c.POINTER(klt_pyr_layout)]),
-    "klt_pyr_build": (_c.c_int, [_P, _P, _c.POINTER(klt_pyr_layout), _P, _P]),
+    "klt_pyr_build": (_c.c_int, [_P, _P, _c.POINTER(klt_pyr_layout), _P, _c.c_int, _c.c_int, _P]),
     "klt_pyr_down": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _P, _c.c_int64, _c.c_int64, _c.c_int, _P]),
-    "klt_lk_track": (_c.c_int, [_P, _P, _P, _P, _P, _c.POINTER(klt_pyr_layout), _P, _P, _P, _P, _P, _c.c_int,
+    "klt_lk_track": (_c.c_int, [_P, _P, _P, _P, _P, _c.POINTER(klt_pyr_layout), _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
                                 _c.POINTER(klt_lk_params), _P]),
     "klt_calc_optical_flow_pyr_lk_host": (_c.c_int, [_P, _P, _c.c_int64, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P,
                                                      _c.c_int, _c.c_int, _c.POINTER(klt_lk_params), _c.POINTER(_c.c_int)]),

@@ -55,16 +55,17 @@ klt_status ensure_host_ws(klt_ctx* ctx, size_t bytes)
     return KLT_OK;
 }
 
-void make_view(const klt_pyr_layout* lay, const uint8_t* img, const uint8_t* pyr, PyrView& v)
+void make_view(const klt_pyr_layout* lay, const uint8_t* img, const uint8_t* pyr, int first_item, int item_stride, PyrView& v)
 {
     v.top = lay->top;
     for (int l = 0; l <= lay->top; ++l) {
         const klt_level& s = lay->level[l];
-        v.lv[l].data = (l == 0) ? img : pyr + s.offset;
-        v.lv[l].batch_stride = s.batch_stride;
+        v.lv[l].data = ((l == 0) ? img : pyr + s.offset) + (int64_t)first_item * s.batch_stride;
+        v.lv[l].batch_stride = s.batch_stride * item_stride;
         v.lv[l].pitch = (int)s.pitch;
         v.lv[l].w = s.w;
         v.lv[l].h = s.h;
+        v.lv[l].aligned4 = (((uintptr_t)v.lv[l].data | (uintptr_t)s.pitch | (uintptr_t)s.batch_stride) & 3) == 0;
     }
 }
 
@@ -210,19 +211,22 @@ klt_status klt_pyr_down(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_
                            ctx->sm_count, (cudaStream_t)stream);
 }
 
-klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* layout, uint8_t* d_pyr, void* stream)
+klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* layout, uint8_t* d_pyr,
+                         int first_item, int n_items, void* stream)
 {
     if (!ctx || !d_img) return KLT_ERR_INVALID_ARG;
     klt_status s = check_layout(layout);
     if (s != KLT_OK) return s;
     if (layout->top > 0 && !d_pyr) return KLT_ERR_INVALID_ARG;
+    if (n_items <= 0) { first_item = 0; n_items = layout->batch; }
+    if (first_item < 0 || first_item + n_items > layout->batch) return KLT_ERR_INVALID_ARG;
     for (int l = 0; l < layout->top; ++l) {
         const klt_level& a = layout->level[l];
         const klt_level& b = layout->level[l + 1];
         if (b.w != (a.w + 1) / 2 || b.h != (a.h + 1) / 2) return KLT_ERR_INVALID_ARG;
-        const uint8_t* src = (l == 0) ? d_img : d_pyr + a.offset;
-        s = pyr_down_launch(src, a.w, a.h, a.pitch, a.batch_stride, d_pyr + b.offset, b.pitch, b.batch_stride,
-                            layout->batch, ctx->sm_count, (cudaStream_t)stream);
+        const uint8_t* src = ((l == 0) ? d_img : d_pyr + a.offset) + (int64_t)first_item * a.batch_stride;
+        s = pyr_down_launch(src, a.w, a.h, a.pitch, a.batch_stride, d_pyr + b.offset + (int64_t)first_item * b.batch_stride,
+                            b.pitch, b.batch_stride, n_items, ctx->sm_count, (cudaStream_t)stream);
         if (s != KLT_OK) return s;
     }
     return KLT_OK;
@@ -230,22 +234,27 @@ klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layou
 
 klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* d_prev_pyr,
                         const uint8_t* d_next_img, const uint8_t* d_next_pyr, const klt_pyr_layout* layout,
+                        int prev_first, int next_first, int pair_stride, int n_pairs,
                         const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
                         int32_t* d_iters, int n_per_pair, const klt_lk_params* params, void* stream)
 {
-    if (!ctx || !params || !d_prev_img || !d_next_img || n_per_pair < 0) return KLT_ERR_INVALID_ARG;
+    if (!ctx || !params || !d_prev_img || !d_next_img || n_per_pair < 0 || n_pairs < 0) return KLT_ERR_INVALID_ARG;
     klt_status s = check_layout(layout);
     if (s != KLT_OK) return s;
+    if (pair_stride < 1 || prev_first < 0 || next_first < 0) return KLT_ERR_INVALID_ARG;
+    if (n_pairs > 0 && ((int64_t)prev_first + (int64_t)(n_pairs - 1) * pair_stride >= layout->batch ||
+                        (int64_t)next_first + (int64_t)(n_pairs - 1) * pair_stride >= layout->batch))
+        return KLT_ERR_INVALID_ARG;
     if (layout->top > 0 && (!d_prev_pyr || !d_next_pyr)) return KLT_ERR_INVALID_ARG;
     if (params->win_w <= 2 || params->win_h <= 2) return KLT_ERR_INVALID_ARG;
-    if (n_per_pair == 0) return KLT_OK;
+    if (n_per_pair == 0 || n_pairs == 0) return KLT_OK;
     if (!d_prev_pts || !d_next_pts || !d_status || !d_err) return KLT_ERR_INVALID_ARG;
     LKLaunch L;
-    make_view(layout, d_prev_img, d_prev_pyr, L.prev);
-    make_view(layout, d_next_img, d_next_pyr, L.next);
+    make_view(layout, d_prev_img, d_prev_pyr, prev_first, pair_stride, L.prev);
+    make_view(layout, d_next_img, d_next_pyr, next_first, pair_stride, L.next);
     L.prev_pts = d_prev_pts; L.next_pts = d_next_pts; L.status = d_status; L.err = d_err; L.iters = d_iters;
     L.n_per_pair = n_per_pair;
-    L.batch = layout->batch;
+    L.batch = n_pairs;
     L.win_w = params->win_w; L.win_h = params->win_h;
     normalise_criteria(params, L.max_count, L.eps2);
     L.flags = params->flags;
@@ -292,19 +301,12 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)
         KLT_CUDA(cudaMemcpyAsync(d_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, st);
+    s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, 0, 0, st);
     if (s != KLT_OK) return s;
-    // LK sees the two images as two single-image pyramids (batch 1) that share one buffer
-    klt_pyr_layout one = lay;
-    one.batch = 1;
-    const uint8_t* prev_pyr = d + off_pyr;
-    const uint8_t* next_pyr = d + off_pyr;  // next image = batch item 1: shift every level by its batch stride
-    PyrView pv, nv;
-    make_view(&one, d + off_img, prev_pyr, pv);
-    make_view(&one, d + off_img + ibytes, next_pyr, nv);
-    for (int l = 1; l <= lay.top; ++l) nv.lv[l].data += lay.level[l].batch_stride;
+    // the pair lives in one batch-2 pyramid: prev = item 0, next = item 1
     LKLaunch L;
-    L.prev = pv; L.next = nv;
+    make_view(&lay, d + off_img, d + off_pyr, 0, 1, L.prev);
+    make_view(&lay, d + off_img, d + off_pyr, 1, 1, L.next);
     L.prev_pts = reinterpret_cast<const float*>(d + off_pts);
     L.next_pts = d_next; L.status = d_status; L.err = d_err; L.iters = nullptr;
     L.n_per_pair = n; L.batch = 1;
@@ -349,7 +351,7 @@ klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img,
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream;
     KLT_CUDA(cudaMemcpy2DAsync(d, ipitch, img, (size_t)pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
-    s = klt_pyr_build(ctx, d, &lay, d + ibytes, st);
+    s = klt_pyr_build(ctx, d, &lay, d + ibytes, 0, 0, st);
     if (s != KLT_OK) return s;
     int64_t o = 0;
     for (int l = 0; l <= lay.top; ++l) {

@@ -16,6 +16,7 @@ struct LevelView {
     long long batch_stride;
     int pitch;
     int w, h;
+    int aligned4;  // data, pitch and batch_stride are multiples of 4: rows may be read with 32-bit loads
 };
 
 struct PyrView {
@@ -60,6 +61,7 @@ struct LKLaunch {
 };
 
 klt_status lk_launch(const LKLaunch& L, int sm_count, cudaStream_t stream);
+klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream);
 klt_status lk_init(int device);
 
 }  // namespace klt

@@ -25,6 +25,7 @@
 #include "klt_common.cuh"
 
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace klt {
 
@@ -631,9 +632,17 @@ klt_status lk_init(int device)
     return KLT_OK;
 }
 
-klt_status lk_launch(const LKLaunch& L, int /*sm_count*/, cudaStream_t stream)
+klt_status lk_launch(const LKLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.win_w <= 2 || L.win_h <= 2) return KLT_ERR_INVALID_ARG;
+    {   // specialised kernels for the common windows; KLT_LK_GENERIC=1 forces the generic one (tests)
+        static const char* force_generic = getenv("KLT_LK_GENERIC");
+        static const char* force_wpp = getenv("KLT_LK_WPP");
+        if (!(force_generic && force_generic[0] == '1')) {
+            const klt_status s = lk_launch_fast(L, sm_count, force_wpp ? atoi(force_wpp) : 0, stream);
+            if (s != KLT_ERR_UNSUPPORTED) return s;
+        }
+    }
     if ((long long)L.win_w * L.win_h > KLT_MAX_WIN_AREA || L.win_w > 504 || L.win_h > 504) return KLT_ERR_UNSUPPORTED;
     const LKGeom G = make_geom(L.win_w, L.win_h);
     if (G.nu >= 4096 || G.nruns >= 4096 || G.g8 > 64 || G.r8 > 64) return KLT_ERR_UNSUPPORTED;

@@ -1,0 +1,755 @@
+// K4 (specialised): fused Scharr + pyramidal LK for compile-time window sizes, WPP warps per point.
+//
+// Same arithmetic as klt_lk.cu (bit-exact with cv2.calcOpticalFlowPyrLK as called
+// at reference src/extractor/extractor.py:44,45,65,66); this variant is what the BASELINE configs
+// (winSize 21 and 31) run.  Differences in structure:
+//  * WPP in {1,2,4} warps cooperate on one keypoint (named barriers), so a 2000-point frame pair fills
+//    the chip and the per-iteration latency of the slowest point -- which bounds the launch -- drops;
+//    WPP = 1 is the throughput shape for large batches.
+//  * the window is cut into 4-pixel units; each thread keeps the Q5 intensity / Q14 derivative patch of
+//    its units in registers for the whole level, only the next-image region lives in shared memory;
+//  * bilinear taps use dp2a (two 14-bit weights x two u8 pixels per instruction, exact);
+//  * neighbourhoods are staged with 32-bit loads (all loads in flight before the first store);
+//  * the mismatch sums are reduced in three tiers: (0) if sum|d|*max(|gx|,|gy|) over the WHOLE window
+//    is <= 2^24 every float32 partial sum OpenCV forms is an exact integer, so b = float(sum) and only
+//    3 values cross the warp(s); (1) otherwise per-accumulation-class sums (4 SIMD lanes + tail) with
+//    the same test per class; (2) otherwise a serial float32 replay in OpenCV's order.
+#include "klt_common.cuh"
+
+namespace klt {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kM = 3;  // margin of the staged next-image region
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kExact = 1 << 24;
+
+__host__ __device__ constexpr int r4(int v) { return (v + 3) / 4 * 4; }
+__host__ __device__ constexpr int r16(int v) { return (v + 15) / 16 * 16; }
+
+template <int WW, int WH, int WPP>
+struct Cfg {
+    static constexpr int UPR = (WW + 3) / 4;          // 4-pixel units per window row
+    static constexpr int NV = 8 * (WW / 8);           // width of OpenCV's SIMD part (A.5)
+    static constexpr int TL = WW - NV;                // scalar tail
+    static constexpr int NU = WH * UPR;
+    static constexpr int NT = 32 * WPP;               // threads per point
+    static constexpr int UPT = (NU + NT - 1) / NT;    // units per thread
+    static constexpr int PPC = kThreads / NT;         // points per CTA
+    static constexpr bool PACK = UPT > 2;             // register budget: pack the per-pixel state
+    static constexpr int SI = r4(WW + 6);             // prev-image region: row stride (bytes)
+    static constexpr int IR = WH + 3;                 //                    rows
+    static constexpr int SD = r4(WW + 2);             // derivative region: row stride (words)
+    static constexpr int DR = WH + 1;
+    static constexpr int JW = WW + 1 + 2 * kM;        // next-image region: logical size
+    static constexpr int JR = WH + 1 + 2 * kM;
+    static constexpr int SJ = r4(JW + 3);             //                    row stride (bytes)
+    static constexpr int RPR = (WW + 1 + 3) / 4;      // Scharr: 4-position runs per row
+    static constexpr int NRUN = DR * RPR;
+    // shared-memory slice of one point (bytes)
+    static constexpr int OFF_J = 0;
+    static constexpr int OFF_D = OFF_J + r16(SJ * JR);        // dreg; fallback: packed derivative patch
+    static constexpr int D_BYTES = r16(4 * (SD * DR > 2 * WW * WH ? SD * DR : 2 * WW * WH));  // replay: 2 x WW*WH ints
+    static constexpr int OFF_I = OFF_D + D_BYTES;             // ireg
+    static constexpr int I_BYTES = r16(SI * IR);
+    static constexpr int NS = NV / 8;                         // 8-pixel SIMD steps per window row
+    static constexpr int OFF_R3 = OFF_I + I_BYTES;            // [2][WPP] int4
+    static constexpr int OFF_R16 = OFF_R3 + 2 * WPP * 16;     // [2][WPP][16] int
+    static constexpr int POINT_BYTES = (OFF_R16 + 2 * WPP * 64 + 127) / 128 * 128;
+};
+
+__device__ __forceinline__ int dp2a_lo(uint32_t w, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t w, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
+
+// Per-pixel patch state of one window pixel: Q5 intensity, Q14 derivative (gx, gy), gm = max(|gx|,|gy|).
+// Plain registers when a thread owns few pixels, two packed registers per pixel otherwise.
+template <bool PACK> struct PxStore;
+template <> struct PxStore<false> {
+    int iv_, gx_, gy_, gm_;
+    __device__ __forceinline__ void set(int iv, int gx, int gy, int gm) { iv_ = iv; gx_ = gx; gy_ = gy; gm_ = gm; }
+    __device__ __forceinline__ int iv() const { return iv_; }
+    __device__ __forceinline__ int gx() const { return gx_; }
+    __device__ __forceinline__ int gy() const { return gy_; }
+    __device__ __forceinline__ int gm() const { return gm_; }
+};
+template <> struct PxStore<true> {
+    uint32_t a_, g_;
+    __device__ __forceinline__ void set(int iv, int gx, int gy, int gm) { a_ = (uint32_t)iv | ((uint32_t)gm << 16); g_ = ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16); }
+    __device__ __forceinline__ int iv() const { return (int)(a_ & 0xffffu); }
+    __device__ __forceinline__ int gx() const { return (int)(short)(g_ & 0xffffu); }
+    __device__ __forceinline__ int gy() const { return ((int)g_) >> 16; }
+    __device__ __forceinline__ int gm() const { return (int)(a_ >> 16); }
+};
+// the 4 mismatch values of one unit
+template <bool PACK> struct DiffStore;
+template <> struct DiffStore<false> {
+    int d_[4];
+    __device__ __forceinline__ void set(int j, int d) { d_[j] = d; }
+    __device__ __forceinline__ int get(int j) const { return d_[j]; }
+};
+template <> struct DiffStore<true> {
+    uint32_t p_[2];
+    __device__ __forceinline__ void set(int j, int d) { if (j & 1) p_[j >> 1] |= (uint32_t)d << 16; else p_[j >> 1] = (uint32_t)d & 0xffffu; }
+    __device__ __forceinline__ int get(int j) const { return (j & 1) ? (((int)p_[j >> 1]) >> 16) : (int)(short)(p_[j >> 1] & 0xffffu); }
+};
+
+template <int WPP>
+__device__ __forceinline__ void point_sync(int bar)
+{
+    if constexpr (WPP == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(32 * WPP) : "memory");
+}
+
+__device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+__device__ __forceinline__ bool floor_in_range(float x, float y, int win_w, int win_h, int lw, int lh, int& ix, int& iy)
+{
+    const bool finite = (fabsf(x) < 1.0e9f) && (fabsf(y) < 1.0e9f);
+    ix = finite ? __float2int_rd(x) : INT_MIN;
+    iy = finite ? __float2int_rd(y) : INT_MIN;
+    return finite && !(ix < -win_w || ix >= lw || iy < -win_h || iy >= lh);
+}
+
+__device__ __forceinline__ float combine5(float q0, float q1, float q2, float q3, float t)
+{
+    const float s = __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3));
+    return __fmul_rn(__fadd_rn(t, s), 9.5367431640625e-07f);
+}
+
+// Stage ROWS x STRIDE bytes whose top-left image coordinate is (ax, y0) (ax % 4 == 0) into smem.  Columns
+// [c0, c0 + need) of every row are the ones later read; the rest may hold anything.
+template <int ROWS, int STRIDE, int NT>
+__device__ __forceinline__ void stage(uint8_t* __restrict__ dst, const LevelView& lv, const uint8_t* __restrict__ img,
+                                      int ax, int y0, int c0, int need, int tid)
+{
+    constexpr int NWR = STRIDE / 4;
+    constexpr int NWORDS = ROWS * NWR;
+    constexpr int PER = (NWORDS + NT - 1) / NT;
+    // 32-bit loads whenever the staged columns lie inside the image; rows are reflected per row (REFLECT_101), which
+    // is the common border case on the small coarse levels.  Only horizontal crossings take the byte path.
+    const bool fast = lv.aligned4 && ax >= 0 && (ax + STRIDE <= lv.w);
+    if (fast) {  // uniform over the point's threads
+        const uint8_t* __restrict__ base = img + ax;
+        const bool rows_inside = (y0 >= 0) && (y0 + ROWS <= lv.h);
+        uint32_t v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * NT;
+            const int r = i / NWR, c = i - r * NWR;
+            const int yy = rows_inside ? (y0 + r) : reflect101(y0 + r, lv.h);
+            v[k] = (i < NWORDS) ? __ldg(reinterpret_cast<const uint32_t*>(base + (long long)yy * lv.pitch) + c) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * NT;
+            if (i < NWORDS) reinterpret_cast<uint32_t*>(dst)[i] = v[k];
+        }
+    } else {
+        for (int i = tid; i < ROWS * need; i += NT) {
+            const int r = i / need, c = c0 + (i - r * need);
+            dst[r * STRIDE + c] = __ldg(img + (long long)reflect101(y0 + r, lv.h) * lv.pitch + reflect101(ax + c, lv.w));
+        }
+    }
+}
+
+// two words holding bytes [o, o+4) and [o+1, o+5) of an smem row (o = arbitrary byte offset)
+__device__ __forceinline__ void load5(const uint8_t* row, int o, uint32_t& a, uint32_t& b)
+{
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row) + (o >> 2);
+    const uint32_t w0 = wp[0], w1 = wp[1];
+    const int s = (o & 3) * 8;
+    a = __funnelshift_r(w0, w1, s);
+    b = __funnelshift_rc(w0, w1, s + 8);
+}
+
+// sum 3 values over all threads of the point; every thread gets the totals (REDUX + one smem exchange)
+template <int WPP>
+__device__ __forceinline__ void point_sum3(int& a, int& b, int& c, int4* red3, int& par3, int wip, int lane, int bar)
+{
+    a = __reduce_add_sync(kFull, a);
+    b = __reduce_add_sync(kFull, b);
+    c = __reduce_add_sync(kFull, c);
+    if constexpr (WPP > 1) {
+        int4* slot = red3 + par3 * WPP;
+        if (lane == 0) slot[wip] = make_int4(a, b, c, 0);
+        point_sync<WPP>(bar);
+        a = 0; b = 0; c = 0;
+#pragma unroll
+        for (int w = 0; w < WPP; ++w) {
+            const int4 v = slot[w];
+            a += v.x; b += v.y; c += v.z;
+        }
+        par3 ^= 1;
+    }
+}
+
+// sum 15 values (v[15] is ignored) over all threads of the point; every thread gets all totals
+template <int WPP>
+__device__ __forceinline__ void point_sum16(int (&v)[16], int* red16, int& par16, int wip, int lane, int bar)
+{
+#pragma unroll
+    for (int i = 0; i < 15; ++i) v[i] = __reduce_add_sync(kFull, v[i]);
+    if constexpr (WPP > 1) {
+        int* slot = red16 + par16 * WPP * 16;
+        if (lane < 4) reinterpret_cast<int4*>(slot + wip * 16)[lane] =
+            make_int4(v[0] * 0 + (lane == 0 ? v[0] : lane == 1 ? v[4] : lane == 2 ? v[8] : v[12]),
+                      (lane == 0 ? v[1] : lane == 1 ? v[5] : lane == 2 ? v[9] : v[13]),
+                      (lane == 0 ? v[2] : lane == 1 ? v[6] : lane == 2 ? v[10] : v[14]),
+                      (lane == 0 ? v[3] : lane == 1 ? v[7] : lane == 2 ? v[11] : 0));
+        point_sync<WPP>(bar);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int4 acc = reinterpret_cast<const int4*>(slot)[q];
+#pragma unroll
+            for (int w = 1; w < WPP; ++w) {
+                const int4 t = reinterpret_cast<const int4*>(slot + w * 16)[q];
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+            v[4 * q] = acc.x; v[4 * q + 1] = acc.y; v[4 * q + 2] = acc.z; v[4 * q + 3] = acc.w;
+        }
+        par16 ^= 1;
+    }
+}
+
+// ---- serial float32 replay in OpenCV's accumulation order -------------------------------
+// Chain-ordered scratch layout of one sum (WW*WH ints): SIMD lane l (x % 4 == l, x < NV) first, row-major
+// inside the lane, then the scalar tail (x >= NV) row-major.
+template <int WW, int WH>
+__device__ __forceinline__ int chain_slot_g(int y, int x)
+{
+    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    return (x < NV) ? (((x & 3) * WH + y) * (NV / 4) + (x >> 2)) : (WH * NV + y * TL + (x - NV));
+}
+// mismatch sums: lane l adds (x0+l, x0+l+4) pairs -> the two halves of a pair sit next to each other
+template <int WW, int WH>
+__device__ __forceinline__ int chain_slot_b(int y, int x)
+{
+    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    return (x < NV) ? ((((x & 3) * WH + y) * (NV / 8) + (x >> 3)) * 2 + ((x >> 2) & 1)) : (WH * NV + y * TL + (x - NV));
+}
+
+// G: lanes 0..14 of ONE warp = 3 sums x (4 SIMD lanes + tail); scratch holds packed (gx | gy << 16) words
+template <int WW, int WH>
+__device__ __forceinline__ void replay_g(const uint32_t* __restrict__ pat, int lane, float& A11, float& A12, float& A22)
+{
+    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    constexpr int LQ = WH * (NV / 4), LT = WH * TL;
+    constexpr int LMAX = LQ > LT ? LQ : LT;
+    const int s = lane / 5, k = lane - 5 * s;
+    const int len = (lane < 15) ? ((k < 4) ? LQ : LT) : 0;
+    const uint32_t* __restrict__ src = pat + ((k < 4) ? k * LQ : 4 * LQ);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < LMAX; ++e) {
+        const uint32_t wd = src[e < len ? e : 0];
+        const int gx = lo16(wd), gy = hi16(wd);
+        const int prod = (s == 0) ? gx * gx : ((s == 1) ? gx * gy : gy * gy);
+        const float nxt = __fadd_rn(acc, (float)prod);
+        acc = (e < len) ? nxt : acc;
+    }
+    float r[3];
+#pragma unroll
+    for (int ss = 0; ss < 3; ++ss)
+        r[ss] = combine5(__shfl_sync(kFull, acc, 5 * ss), __shfl_sync(kFull, acc, 5 * ss + 1), __shfl_sync(kFull, acc, 5 * ss + 2),
+                         __shfl_sync(kFull, acc, 5 * ss + 3), __shfl_sync(kFull, acc, 5 * ss + 4));
+    A11 = r[0]; A12 = r[1]; A22 = r[2];
+}
+
+// b: lanes 0..9 of ONE warp = 2 sums x (4 SIMD lanes + tail); scratch holds the integer products d*g of
+// sum 0 in [0, WW*WH) and of sum 1 in [WW*WH, 2*WW*WH), chain-ordered (chain_slot_b)
+template <int WW, int WH>
+__device__ __forceinline__ void replay_b(const int* __restrict__ prod, int lane, float& b1, float& b2)
+{
+    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    constexpr int LQ = WH * (NV / 8);          // pairs per SIMD-lane chain
+    constexpr int LT2 = (WH * TL + 1) / 2;     // tail elements, two per step
+    constexpr int LMAX = LQ > LT2 ? LQ : LT2;
+    const int s = lane / 5, k = lane - 5 * s;
+    const bool isq = k < 4;
+    const int n_el = (lane < 10) ? (isq ? 2 * LQ : WH * TL) : 0;   // ints this lane consumes
+    const int* __restrict__ src = prod + ((lane < 10) ? s * (WW * WH) + (isq ? k * 2 * LQ : WH * NV) : 0);  // idle lanes read slot 0
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < LMAX; ++e) {
+        const bool in0 = 2 * e < n_el, in1 = 2 * e + 1 < n_el;
+        const int a = src[in0 ? 2 * e : 0], b = src[in1 ? 2 * e + 1 : 0];
+        const float f0 = __fadd_rn(acc, (float)(isq ? a + b : a));
+        acc = in0 ? f0 : acc;
+        const float f1 = __fadd_rn(acc, (float)b);
+        acc = (!isq && in1) ? f1 : acc;
+    }
+    b1 = combine5(__shfl_sync(kFull, acc, 0), __shfl_sync(kFull, acc, 1), __shfl_sync(kFull, acc, 2), __shfl_sync(kFull, acc, 3),
+                  __shfl_sync(kFull, acc, 4));
+    b2 = combine5(__shfl_sync(kFull, acc, 5), __shfl_sync(kFull, acc, 6), __shfl_sync(kFull, acc, 7), __shfl_sync(kFull, acc, 8),
+                  __shfl_sync(kFull, acc, 9));
+}
+
+template <int WW, int WH, int WPP>
+__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
+lk_fast_kernel(const __grid_constant__ LKLaunch L)
+{
+    using C = Cfg<WW, WH, WPP>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int pic = threadIdx.x / C::NT;        // point within the CTA
+    const int tid = threadIdx.x - pic * C::NT;  // thread within the point
+    const int wip = tid >> 5;                   // warp within the point
+    const int bar = 1 + pic;
+    const long long gid = (long long)blockIdx.x * C::PPC + pic;
+    const long long total = (long long)L.n_per_pair * L.batch;
+    if (gid >= total) return;  // uniform over the point's warps: its named barrier is never used
+    const int bidx = (int)(gid / L.n_per_pair);
+
+    uint8_t* ws = smem + pic * C::POINT_BYTES;
+    uint8_t* jreg = ws + C::OFF_J;
+    uint32_t* dreg = reinterpret_cast<uint32_t*>(ws + C::OFF_D);
+    uint8_t* ireg = ws + C::OFF_I;
+    int4* red3 = reinterpret_cast<int4*>(ws + C::OFF_R3);
+    int* red16 = reinterpret_cast<int*>(ws + C::OFF_R16);
+    int par3 = 0, par16 = 0;
+
+    // units of this thread: unit u = tid + k*NT covers window pixels (y, x0..x0+3); coordinates are recomputed where
+    // needed (division by a constant), only the word offset inside the staged next-image region is kept.
+    auto unit_y = [&](int k) { const int u = tid + k * C::NT; return (u < C::NU ? u : 0) / C::UPR; };
+    auto unit_x0 = [&](int k) { const int u = tid + k * C::NT; const int uu = (u < C::NU ? u : 0); return 4 * (uu - (uu / C::UPR) * C::UPR); };
+    auto unit_ok = [&](int k) { return tid + k * C::NT < C::NU; };
+    int jw[C::UPT];
+#pragma unroll
+    for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
+
+    const long long t_start = clock64();
+    int n_t1 = 0, n_t2 = 0;
+    const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
+    float2 outp = make_float2(0.f, 0.f);
+    if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) outp = reinterpret_cast<const float2*>(L.next_pts)[gid];
+    int status = 1;
+    float err = 0.f;
+    int iters = 0;
+    const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
+    const int top = L.prev.top;
+
+    for (int level = top; level >= 0; --level) {
+        const LevelView lvI = L.prev.lv[level];
+        const LevelView lvJ = L.next.lv[level];
+        const uint8_t* __restrict__ imgI = lvI.data + (long long)bidx * lvI.batch_stride;
+        const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
+        const int lw = lvI.w, lh = lvI.h;
+        const float scale = __int_as_float((127 - level) << 23);
+
+        float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
+        float nx, ny;
+        if (level == top) {
+            if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(outp.x, scale); ny = __fmul_rn(outp.y, scale); }
+            else { nx = px; ny = py; }
+        } else {
+            nx = __fmul_rn(outp.x, 2.f); ny = __fmul_rn(outp.y, 2.f);
+        }
+        outp = make_float2(nx, ny);
+
+        px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+        int ipx, ipy;
+        if (!floor_in_range(px, py, WW, WH, lw, lh, ipx, ipy)) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+        // ---- stage both neighbourhoods; the previous level's readers are done (barrier below) -------------
+        point_sync<WPP>(bar);
+        int jax = 0, jy0 = 0, jx0 = 0;  // region origin: smem col 0 <-> image x = jax; window columns start at jx0
+        bool jvalid = false;
+        {
+            int inx, iny;
+            if (floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
+                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
+                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
+            }
+        }
+        const int iax = (ipx - 1) & ~3;
+        const int oi = (ipx - 1) - iax;
+        stage<C::IR, C::SI, C::NT>(ireg, lvI, imgI, iax, ipy - 1, oi, WW + 3, tid);
+        point_sync<WPP>(bar);
+
+        // ---- Scharr derivative at the (WW+1) x (WH+1) integer positions the patch touches -----------------
+        for (int u = tid; u < C::NRUN; u += C::NT) {
+            const int dy = u / C::RPR;
+            const int dx0 = 4 * (u - dy * C::RPR);
+            const uint8_t* r0 = ireg + dy * C::SI + oi + dx0;
+            const uint8_t* r1 = r0 + C::SI;
+            const uint8_t* r2 = r1 + C::SI;
+            int t0[6], t1[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int a = r0[k], b = r1[k], cc = r2[k];
+                t0[k] = 3 * (a + cc) + 10 * b;
+                t1[k] = cc - a;
+            }
+            const bool yin = (unsigned)(ipy + dy) < (unsigned)lh;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dx = dx0 + k;
+                const int gx = t0[k + 2] - t0[k];
+                const int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
+                const bool in = yin && ((unsigned)(ipx + dx) < (unsigned)lw);
+                if (dx < C::SD) dreg[dy * C::SD + dx] = in ? (((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16)) : 0u;
+            }
+        }
+        point_sync<WPP>(bar);
+
+        // ---- patch pass: per-thread register patch + integer class sums of G ------------------------------
+        const uint32_t W0 = (uint32_t)(w00 & 0xffff) | ((uint32_t)w01 << 16);
+        const uint32_t W1 = (uint32_t)(w10 & 0xffff) | ((uint32_t)w11 << 16);
+        PxStore<C::PACK> pxs[C::UPT][4];
+        int vals[16];
+        {
+            unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, t11 = 0, t22 = 0;
+            int q12[4] = {0, 0, 0, 0}, t12 = 0;
+#pragma unroll
+            for (int k = 0; k < C::UPT; ++k) {
+                const int y = unit_y(k), x0 = unit_x0(k);
+                const bool ok = unit_ok(k);
+                uint32_t a0, b0, a1, b1;
+                load5(ireg + (y + 1) * C::SI, oi + 1 + x0, a0, b0);
+                load5(ireg + (y + 2) * C::SI, oi + 1 + x0, a1, b1);
+                int iv[4];
+                iv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                iv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
+                iv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                iv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
+                const uint32_t* d0 = dreg + y * C::SD + x0;
+                const uint32_t* d1 = d0 + C::SD;
+                const uint4 e0 = *reinterpret_cast<const uint4*>(d0);
+                const uint4 e1 = *reinterpret_cast<const uint4*>(d1);
+                const uint32_t r0w[5] = {e0.x, e0.y, e0.z, e0.w, d0[4]};
+                const uint32_t r1w[5] = {e1.x, e1.y, e1.z, e1.w, d1[4]};
+                unsigned u11[4], u22[4];
+                int u12[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int gx = (lo16(r0w[j]) * w00 + lo16(r0w[j + 1]) * w01 + lo16(r1w[j]) * w10 + lo16(r1w[j + 1]) * w11 + (1 << 13)) >> 14;
+                    int gy = (hi16(r0w[j]) * w00 + hi16(r0w[j + 1]) * w01 + hi16(r1w[j]) * w10 + hi16(r1w[j + 1]) * w11 + (1 << 13)) >> 14;
+                    const bool valid = ok && (x0 + j) < WW;
+                    gx = valid ? gx : 0; gy = valid ? gy : 0;
+                    pxs[k][j].set(valid ? iv[j] : 0, gx, gy, max(abs(gx), abs(gy)));
+                    u11[j] = (unsigned)(gx * gx); u12[j] = gx * gy; u22[j] = (unsigned)(gy * gy);
+                }
+                const bool tail = x0 >= C::NV;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    q11[j] += tail ? 0u : u11[j];
+                    q12[j] += tail ? 0 : u12[j];
+                    q22[j] += tail ? 0u : u22[j];
+                }
+                t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
+                t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
+                t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
+            }
+            const unsigned cap = (1u << 25) / WPP;  // keeps the point-wide totals below 2^31
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                vals[j] = (int)min(q11[j], cap);
+                vals[5 + j] = max(min(q12[j], (int)cap), -(int)cap);
+                vals[10 + j] = (int)min(q22[j], cap);
+            }
+            vals[4] = (int)min(t11, cap);
+            vals[9] = max(min(t12, (int)cap), -(int)cap);
+            vals[14] = (int)min(t22, cap);
+            vals[15] = 0;
+        }
+        point_sum16<WPP>(vals, red16, par16, wip, lane, bar);
+
+        float A11, A12, A22;
+        {
+            // A11 / A22: non-negative terms, exact iff every class total <= 2^24; A12: |gx gy| <= (gx^2 + gy^2) / 2
+            bool exact = true;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                exact = exact && ((unsigned)vals[k] <= (unsigned)kExact) && ((unsigned)vals[10 + k] <= (unsigned)kExact) &&
+                        ((unsigned)vals[k] + (unsigned)vals[10 + k] <= 2u * (unsigned)kExact);
+            if (exact) {
+                A11 = combine5((float)vals[0], (float)vals[1], (float)vals[2], (float)vals[3], (float)vals[4]);
+                A12 = combine5((float)vals[5], (float)vals[6], (float)vals[7], (float)vals[8], (float)vals[9]);
+                A22 = combine5((float)vals[10], (float)vals[11], (float)vals[12], (float)vals[13], (float)vals[14]);
+            } else {
+                // serial replay in OpenCV's order (A.5) from a chain-ordered smem copy of the derivative patch
+                uint32_t* dpat = dreg;  // dreg is dead (everyone passed the point_sum16 barrier)
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k)
+                    if (unit_ok(k)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (unit_x0(k) + j < WW)
+                                dpat[chain_slot_g<WW, WH>(unit_y(k), unit_x0(k) + j)] =
+                                    ((uint32_t)pxs[k][j].gx() & 0xffffu) | ((uint32_t)pxs[k][j].gy() << 16);
+                    }
+                point_sync<WPP>(bar);
+                replay_g<WW, WH>(dpat, lane, A11, A12, A22);  // every warp of the point computes the same values
+            }
+        }
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)));
+        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), rad), (float)(2 * WW * WH));
+        if (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) err = min_eig;
+        if (min_eig < L.min_eig_thr || D < 1.1920929e-7f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+        // ---- iterations ------------------------------------------------------------------------------------
+        // make sure the staged next-image region covers the window at (inx, iny)
+        auto ensure_j = [&](int inx, int iny) {
+            if (!jvalid || inx < jx0 || iny < jy0 || inx + WW + 1 > jx0 + C::JW || iny + WH + 1 > jy0 + C::JR) {
+                point_sync<WPP>(bar);
+                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
+                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
+                point_sync<WPP>(bar);
+            }
+        };
+
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < L.max_count; ++j) {
+            int inx, iny;
+            if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
+                if (level == 0) status = 0;
+                break;
+            }
+            ++iters;
+            ensure_j(inx, iny);
+            int v00, v01, v10, v11;
+            q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
+            const uint32_t W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
+            const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
+            DiffStore<C::PACK> dd[C::UPT];
+            int s1, s2, bnd;
+            {
+                // invalid pixels carry gx = gy = gm = 0, so they drop out of all three sums without a select
+                const int cb = (iny - jy0) * C::SJ + (inx - jax);
+                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
+                const int sh = (cb & 3) * 8;
+                s1 = 0; s2 = 0; bnd = 0;
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const uint32_t* __restrict__ r0 = jbase + jw[k];
+                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
+                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
+                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
+                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_rc(q0, q1, sh + 8);
+                    int jv[4];
+                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                    jv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
+                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                    jv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int d = jv[jj] - pxs[k][jj].iv();
+                        dd[k].set(jj, d);
+                        s1 += d * pxs[k][jj].gx();
+                        s2 += d * pxs[k][jj].gy();
+                        bnd += abs(d) * pxs[k][jj].gm();
+                    }
+                }
+            }
+            // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 16; clamp so the point total cannot wrap
+            bnd = min(bnd, (1 << 25) / WPP);
+            point_sum3<WPP>(s1, s2, bnd, red3, par3, wip, lane, bar);
+            float b1, b2;
+            if (bnd <= kExact) {
+                // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
+                b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
+                b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
+            } else {
+                // tier 1: per accumulation class
+                ++n_t1;
+                int cv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cv[i] = 0;
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    int u1[4], u2[4], ub[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int d = dd[k].get(jj);
+                        u1[jj] = d * pxs[k][jj].gx();
+                        u2[jj] = d * pxs[k][jj].gy();
+                        ub[jj] = (abs(d) * pxs[k][jj].gm() + 15) >> 4;
+                    }
+                    const bool tail = unit_x0(k) >= C::NV;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        cv[jj] += tail ? 0 : u1[jj];
+                        cv[5 + jj] += tail ? 0 : u2[jj];
+                        cv[10 + jj] += tail ? 0 : ub[jj];
+                    }
+                    cv[4] += tail ? (u1[0] + u1[1] + u1[2] + u1[3]) : 0;
+                    cv[9] += tail ? (u2[0] + u2[1] + u2[2] + u2[3]) : 0;
+                    cv[14] += tail ? (ub[0] + ub[1] + ub[2] + ub[3]) : 0;
+                }
+#pragma unroll
+                for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (1 << 22) / WPP);
+                point_sum16<WPP>(cv, red16, par16, wip, lane, bar);
+                bool exact = true;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) exact = exact && (cv[10 + k] <= (kExact >> 4));
+                if (exact) {
+                    b1 = combine5((float)cv[0], (float)cv[1], (float)cv[2], (float)cv[3], (float)cv[4]);
+                    b2 = combine5((float)cv[5], (float)cv[6], (float)cv[7], (float)cv[8], (float)cv[9]);
+                } else {
+                    // tier 2: serial replay (pairs (l, l+4) summed in int32 first; A.5)
+                    ++n_t2;
+                    int* prod = reinterpret_cast<int*>(dreg);
+#pragma unroll
+                    for (int k = 0; k < C::UPT; ++k)
+                        if (unit_ok(k)) {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (unit_x0(k) + jj < WW) {
+                                    const int slot = chain_slot_b<WW, WH>(unit_y(k), unit_x0(k) + jj);
+                                    const int d = dd[k].get(jj);
+                                    prod[slot] = d * pxs[k][jj].gx();
+                                    prod[WW * WH + slot] = d * pxs[k][jj].gy();
+                                }
+                        }
+                    point_sync<WPP>(bar);
+                    replay_b<WW, WH>(prod, lane, b1, b2);  // every warp of the point computes the same values
+                    point_sync<WPP>(bar);  // scratch is rewritten by the next replay only after everyone is here
+                }
+            }
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            outp = make_float2(__fadd_rn(nx, hwx), __fadd_rn(ny, hwy));
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                outp.x = __fsub_rn(outp.x, __fmul_rn(dx, 0.5f));
+                outp.y = __fsub_rn(outp.y, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+
+        // ---- err at level 0 ------------------------------------------------------------------------------------
+        if (status && level == 0 && (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) == 0) {
+            const float qx = __fsub_rn(outp.x, hwx), qy = __fsub_rn(outp.y, hwy);
+            int iqx, iqy;
+            if (!floor_in_range(qx, qy, WW, WH, lw, lh, iqx, iqy)) {
+                status = 0;
+                continue;
+            }
+            ensure_j(iqx, iqy);
+            int v00, v01, v10, v11;
+            q14_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), v00, v01, v10, v11);
+            const uint32_t W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
+            const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
+            int e = 0, z1 = 0, z2 = 0;
+            {
+                const int cb = (iqy - jy0) * C::SJ + (iqx - jax);
+                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
+                const int sh = (cb & 3) * 8;
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const uint32_t* __restrict__ r0 = jbase + jw[k];
+                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
+                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
+                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
+                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_rc(q0, q1, sh + 8);
+                    int jv[4];
+                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                    jv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
+                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                    jv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
+                    const bool ok = unit_ok(k);
+                    const int x0 = unit_x0(k);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) e += (ok && (x0 + jj) < WW) ? abs(jv[jj] - pxs[k][jj].iv()) : 0;
+                }
+            }
+            point_sum3<WPP>(e, z1, z2, red3, par3, wip, lane, bar);
+            // |d| <= 8160 and WW*WH <= 2056 for the instantiated windows: e <= 2^24, so OpenCV's float32 running sum is exact
+            err = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * WW * WH));
+        }
+    }
+
+    if (tid == 0) {
+        reinterpret_cast<float2*>(L.next_pts)[gid] = outp;
+        L.status[gid] = (uint8_t)status;
+        L.err[gid] = err;
+        if (L.iters) {
+            // debug flag 0x100: cycles / 64 in the low 20 bits, tier-1 and tier-2 counts above (profiling aid)
+            L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
+        }
+    }
+}
+
+template <int WW, int WH, int WPP>
+klt_status launch_fast(const LKLaunch& L, cudaStream_t stream)
+{
+    using C = Cfg<WW, WH, WPP>;
+    static_assert(WW * WH <= 2056, "err pass assumes an exact float32 sum");
+    static_assert(C::UPT <= 8, "per-thread bound accumulators would overflow");
+    static bool configured = false;
+    const size_t smem = (size_t)C::POINT_BYTES * C::PPC;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lk_fast_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (klt_status)e;
+        configured = true;
+    }
+    const long long total = (long long)L.n_per_pair * L.batch;
+    const long long blocks = (total + C::PPC - 1) / C::PPC;
+    if (blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    lk_fast_kernel<WW, WH, WPP><<<(unsigned)blocks, kThreads, smem, stream>>>(L);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+template <int WW, int WH>
+klt_status launch_wpp(const LKLaunch& L, int wpp, cudaStream_t stream)
+{
+    switch (wpp) {
+        case 1: return launch_fast<WW, WH, 1>(L, stream);
+        case 2: return launch_fast<WW, WH, 2>(L, stream);
+        default: return launch_fast<WW, WH, 4>(L, stream);
+    }
+}
+
+}  // namespace
+
+// Returns KLT_ERR_UNSUPPORTED when no specialisation exists (the caller then uses the generic kernel).
+klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream)
+{
+    const long long total = (long long)L.n_per_pair * L.batch;
+    // warps per point: fill the chip once (about 32 resident warps per SM), then prefer fewer warps per point
+    int wpp = 1;
+    const long long resident = (long long)sm_count * 32;
+    if (total * 4 <= resident * 2) wpp = 4;
+    else if (total * 2 <= resident * 2) wpp = 2;
+    if (forced_wpp == 1 || forced_wpp == 2 || forced_wpp == 4) wpp = forced_wpp;
+    if (L.win_w == 21 && L.win_h == 21) return launch_wpp<21, 21>(L, wpp, stream);
+    if (L.win_w == 31 && L.win_h == 31) return launch_wpp<31, 31>(L, wpp, stream);
+    return KLT_ERR_UNSUPPORTED;
+}
+
+}  // namespace klt

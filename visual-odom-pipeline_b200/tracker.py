@@ -80,7 +80,7 @@ class DevicePyramid:
         """(Re)build levels 1..top from self.images on the current torch stream."""
         L = _lib.load()
         rc = L.klt_pyr_build(self.ctx.handle, self.images.data_ptr(), ctypes.byref(self.layout), self.buffer.data_ptr(),
-                             _stream_ptr(self.images))
+                             0, 0, _stream_ptr(self.images))
         if rc != KLT_OK:
             _raise_status(rc, "klt_pyr_build")
         return self
@@ -134,7 +134,7 @@ def lk_track(prev, nxt, prevPts, nextPts=None, criteria=(3, 30, 0.01), flags=0, 
         params = make_params(prev.win, criteria, flags, minEigThreshold)
         L = _lib.load()
         rc = L.klt_lk_track(prev.ctx.handle, prev.images.data_ptr(), prev.buffer.data_ptr(), nxt.images.data_ptr(),
-                            nxt.buffer.data_ptr(), ctypes.byref(prev.layout), pts.data_ptr(), out.data_ptr(),
+                            nxt.buffer.data_ptr(), ctypes.byref(prev.layout), 0, 0, 1, B, pts.data_ptr(), out.data_ptr(),
                             status.data_ptr(), err.data_ptr(), iters.data_ptr() if return_iters else None, N,
                             ctypes.byref(params), _stream_ptr(pts))
         if rc != KLT_OK:
