@@ -28,6 +28,31 @@ constexpr int kExact = 1 << 24;
 __host__ __device__ constexpr int r4(int v) { return (v + 3) / 4 * 4; }
 __host__ __device__ constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 
+// ---- serial float32 replay in OpenCV's accumulation order (SURVEY.md A.5) -------------------------------
+// Scratch layout: one zero-padded row per accumulation chain (4 SIMD lanes with x % 4 == l, x < NV, then the scalar
+// tail x >= NV), elements in OpenCV's visiting order.  Padding with zeros makes every chain the same length, so the
+// replay loop has no bounds checks: adding +0.0f is an exact no-op (the accumulator is never -0).
+template <int WW, int WH>
+struct Chains {
+    static constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    // G: one element per pixel
+    static constexpr int GQ = WH * (NV / 4), GT = WH * TL;
+    static constexpr int GLEN = (GQ > GT ? GQ : GT);                 // padded chain length (words)
+    static constexpr int G_WORDS = 5 * GLEN;
+    // b: SIMD lanes consume (x, x+4) pairs, the tail single pixels; both stored as ints, two per step
+    static constexpr int BQ = 2 * WH * (NV / 8), BT = WH * TL;
+    static constexpr int BLEN = ((BQ > BT ? BQ : BT) + 1) / 2 * 2;   // padded chain length (ints, even)
+    static constexpr int B_WORDS = 10 * BLEN;
+    __device__ static __forceinline__ int slot_g(int y, int x)
+    {
+        return (x < NV) ? ((x & 3) * GLEN + y * (NV / 4) + (x >> 2)) : (4 * GLEN + y * TL + (x - NV));
+    }
+    __device__ static __forceinline__ int slot_b(int y, int x)   // within one sum (add 5 * BLEN for the second)
+    {
+        return (x < NV) ? ((x & 3) * BLEN + (y * (NV / 8) + (x >> 3)) * 2 + ((x >> 2) & 1)) : (4 * BLEN + y * TL + (x - NV));
+    }
+};
+
 template <int WW, int WH, int WPP>
 struct Cfg {
     static constexpr int UPR = (WW + 3) / 4;          // 4-pixel units per window row
@@ -50,13 +75,14 @@ struct Cfg {
     // shared-memory slice of one point (bytes)
     static constexpr int OFF_J = 0;
     static constexpr int OFF_D = OFF_J + r16(SJ * JR);        // dreg; fallback: packed derivative patch
-    static constexpr int D_BYTES = r16(4 * (SD * DR > 2 * WW * WH ? SD * DR : 2 * WW * WH));  // replay: 2 x WW*WH ints
+    static constexpr int CHAIN_WORDS = Chains<WW, WH>::B_WORDS > Chains<WW, WH>::G_WORDS ? Chains<WW, WH>::B_WORDS : Chains<WW, WH>::G_WORDS;
+    static constexpr int D_BYTES = r16(4 * (SD * DR > CHAIN_WORDS ? SD * DR : CHAIN_WORDS));  // dreg, or the replay chains
     static constexpr int OFF_I = OFF_D + D_BYTES;             // ireg
     static constexpr int I_BYTES = r16(SI * IR);
     static constexpr int NS = NV / 8;                         // 8-pixel SIMD steps per window row
     static constexpr int OFF_R3 = OFF_I + I_BYTES;            // [2][WPP] int4
-    static constexpr int OFF_R16 = OFF_R3 + 2 * WPP * 16;     // [2][WPP][16] int
-    static constexpr int POINT_BYTES = (OFF_R16 + 2 * WPP * 64 + 127) / 128 * 128;
+    static constexpr int OFF_R16 = OFF_R3 + 2 * WPP * 16;     // [2][16 values][4 warps] int
+    static constexpr int POINT_BYTES = (OFF_R16 + 2 * 256 + 127) / 128 * 128;
 };
 
 __device__ __forceinline__ int dp2a_lo(uint32_t w, uint32_t b, int c)
@@ -203,69 +229,67 @@ __device__ __forceinline__ void point_sum3(int& a, int& b, int& c, int4* red3, i
     }
 }
 
-// sum 15 values (v[15] is ignored) over all threads of the point; every thread gets all totals
+// Sum 15 values over all threads of the point.  Returns, in lane L < 15 of EVERY warp, the point-wide total of
+// value L (one REDUX per value, then one value-major smem exchange so a lane fetches its partials with one load).
 template <int WPP>
-__device__ __forceinline__ void point_sum16(int (&v)[16], int* red16, int& par16, int wip, int lane, int bar)
+__device__ __forceinline__ int point_sum15_lane(const int (&v)[16], int* red16, int& par16, int wip, int lane, int bar)
 {
+    int mine = 0;
 #pragma unroll
-    for (int i = 0; i < 15; ++i) v[i] = __reduce_add_sync(kFull, v[i]);
+    for (int i = 0; i < 15; ++i) {
+        const int t = __reduce_add_sync(kFull, v[i]);
+        mine = (lane == i) ? t : mine;
+    }
     if constexpr (WPP > 1) {
-        int* slot = red16 + par16 * WPP * 16;
-        if (lane < 4) reinterpret_cast<int4*>(slot + wip * 16)[lane] =
-            make_int4(v[0] * 0 + (lane == 0 ? v[0] : lane == 1 ? v[4] : lane == 2 ? v[8] : v[12]),
-                      (lane == 0 ? v[1] : lane == 1 ? v[5] : lane == 2 ? v[9] : v[13]),
-                      (lane == 0 ? v[2] : lane == 1 ? v[6] : lane == 2 ? v[10] : v[14]),
-                      (lane == 0 ? v[3] : lane == 1 ? v[7] : lane == 2 ? v[11] : 0));
+        int* slot = red16 + par16 * 64;
+        if (lane < 15) slot[lane * 4 + wip] = mine;
         point_sync<WPP>(bar);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int4 acc = reinterpret_cast<const int4*>(slot)[q];
-#pragma unroll
-            for (int w = 1; w < WPP; ++w) {
-                const int4 t = reinterpret_cast<const int4*>(slot + w * 16)[q];
-                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-            v[4 * q] = acc.x; v[4 * q + 1] = acc.y; v[4 * q + 2] = acc.z; v[4 * q + 3] = acc.w;
-        }
+        const int4 t = reinterpret_cast<const int4*>(slot)[lane & 15];
+        mine = t.x + t.y + (WPP > 2 ? t.z + t.w : 0);
         par16 ^= 1;
+    }
+    return mine;
+}
+
+// zero the padding of the chain rows (NT threads of one point)
+template <int WW, int WH, int NT>
+__device__ __forceinline__ void zero_pad_g(uint32_t* pat, int tid)
+{
+    using CH = Chains<WW, WH>;
+    constexpr int PQ = CH::GLEN - CH::GQ, PT = CH::GLEN - CH::GT;
+    for (int i = tid; i < 4 * PQ + PT; i += NT) {
+        const int k = (i < 4 * PQ) ? i / (PQ > 0 ? PQ : 1) : 4;
+        const int o = (i < 4 * PQ) ? i - k * PQ : i - 4 * PQ;
+        pat[k * CH::GLEN + (k < 4 ? CH::GQ : CH::GT) + o] = 0u;
+    }
+}
+template <int WW, int WH, int NT>
+__device__ __forceinline__ void zero_pad_b(int* prod, int tid)
+{
+    using CH = Chains<WW, WH>;
+    constexpr int PQ = CH::BLEN - CH::BQ, PT = CH::BLEN - CH::BT;
+    for (int i = tid; i < 2 * (4 * PQ + PT); i += NT) {
+        const int s = i / (4 * PQ + PT), r = i - s * (4 * PQ + PT);
+        const int k = (r < 4 * PQ) ? r / (PQ > 0 ? PQ : 1) : 4;
+        const int o = (r < 4 * PQ) ? r - k * PQ : r - 4 * PQ;
+        prod[(s * 5 + k) * CH::BLEN + (k < 4 ? CH::BQ : CH::BT) + o] = 0;
     }
 }
 
-// ---- serial float32 replay in OpenCV's accumulation order (SURVEY.md A.5) -------------------------------
-// Chain-ordered scratch layout of one sum (WW*WH ints): SIMD lane l (x % 4 == l, x < NV) first, row-major
-// inside the lane, then the scalar tail (x >= NV) row-major.
-template <int WW, int WH>
-__device__ __forceinline__ int chain_slot_g(int y, int x)
-{
-    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
-    return (x < NV) ? (((x & 3) * WH + y) * (NV / 4) + (x >> 2)) : (WH * NV + y * TL + (x - NV));
-}
-// mismatch sums: lane l adds (x0+l, x0+l+4) pairs -> the two halves of a pair sit next to each other
-template <int WW, int WH>
-__device__ __forceinline__ int chain_slot_b(int y, int x)
-{
-    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
-    return (x < NV) ? ((((x & 3) * WH + y) * (NV / 8) + (x >> 3)) * 2 + ((x >> 2) & 1)) : (WH * NV + y * TL + (x - NV));
-}
-
-// G: lanes 0..14 of ONE warp = 3 sums x (4 SIMD lanes + tail); scratch holds packed (gx | gy << 16) words
+// G: lanes 0..14 of ONE warp = 3 sums x (4 SIMD lanes + tail); scratch rows hold packed (gx | gy << 16) words
 template <int WW, int WH>
 __device__ __forceinline__ void replay_g(const uint32_t* __restrict__ pat, int lane, float& A11, float& A12, float& A22)
 {
-    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
-    constexpr int LQ = WH * (NV / 4), LT = WH * TL;
-    constexpr int LMAX = LQ > LT ? LQ : LT;
-    const int s = lane / 5, k = lane - 5 * s;
-    const int len = (lane < 15) ? ((k < 4) ? LQ : LT) : 0;
-    const uint32_t* __restrict__ src = pat + ((k < 4) ? k * LQ : 4 * LQ);
+    using CH = Chains<WW, WH>;
+    const int s = (lane < 15) ? lane / 5 : 0, k = (lane < 15) ? lane - 5 * (lane / 5) : 0;
+    const uint32_t* __restrict__ src = pat + k * CH::GLEN;
     float acc = 0.f;
 #pragma unroll 8
-    for (int e = 0; e < LMAX; ++e) {
-        const uint32_t wd = src[e < len ? e : 0];
+    for (int e = 0; e < CH::GLEN; ++e) {
+        const uint32_t wd = src[e];
         const int gx = lo16(wd), gy = hi16(wd);
-        const int prod = (s == 0) ? gx * gx : ((s == 1) ? gx * gy : gy * gy);
-        const float nxt = __fadd_rn(acc, (float)prod);
-        acc = (e < len) ? nxt : acc;
+        const int prod = ((s == 0) ? gx : gy) * ((s == 2) ? gy : gx);   // gx*gx, gy*gx, gy*gy
+        acc = __fadd_rn(acc, (float)prod);
     }
     float r[3];
 #pragma unroll
@@ -275,28 +299,20 @@ __device__ __forceinline__ void replay_g(const uint32_t* __restrict__ pat, int l
     A11 = r[0]; A12 = r[1]; A22 = r[2];
 }
 
-// b: lanes 0..9 of ONE warp = 2 sums x (4 SIMD lanes + tail); scratch holds the integer products d*g of
-// sum 0 in [0, WW*WH) and of sum 1 in [WW*WH, 2*WW*WH), chain-ordered (chain_slot_b)
+// b: lanes 0..9 of ONE warp = 2 sums x (4 SIMD lanes + tail); scratch rows hold the integer products d*g
 template <int WW, int WH>
 __device__ __forceinline__ void replay_b(const int* __restrict__ prod, int lane, float& b1, float& b2)
 {
-    constexpr int NV = 8 * (WW / 8), TL = WW - NV;
-    constexpr int LQ = WH * (NV / 8);          // pairs per SIMD-lane chain
-    constexpr int LT2 = (WH * TL + 1) / 2;     // tail elements, two per step
-    constexpr int LMAX = LQ > LT2 ? LQ : LT2;
-    const int s = lane / 5, k = lane - 5 * s;
-    const bool isq = k < 4;
-    const int n_el = (lane < 10) ? (isq ? 2 * LQ : WH * TL) : 0;   // ints this lane consumes
-    const int* __restrict__ src = prod + ((lane < 10) ? s * (WW * WH) + (isq ? k * 2 * LQ : WH * NV) : 0);  // idle lanes read slot 0
+    using CH = Chains<WW, WH>;
+    const int c = (lane < 10) ? lane : 0;
+    const int pairmask = ((c % 5) < 4) ? -1 : 0;   // SIMD lanes add the two halves of a pair in int32 first
+    const int2* __restrict__ src = reinterpret_cast<const int2*>(prod + c * CH::BLEN);
     float acc = 0.f;
 #pragma unroll 8
-    for (int e = 0; e < LMAX; ++e) {
-        const bool in0 = 2 * e < n_el, in1 = 2 * e + 1 < n_el;
-        const int a = src[in0 ? 2 * e : 0], b = src[in1 ? 2 * e + 1 : 0];
-        const float f0 = __fadd_rn(acc, (float)(isq ? a + b : a));
-        acc = in0 ? f0 : acc;
-        const float f1 = __fadd_rn(acc, (float)b);
-        acc = (!isq && in1) ? f1 : acc;
+    for (int e = 0; e < CH::BLEN / 2; ++e) {
+        const int2 v = src[e];
+        acc = __fadd_rn(acc, (float)(v.x + (v.y & pairmask)));
+        acc = __fadd_rn(acc, (float)(v.y & ~pairmask));
     }
     b1 = combine5(__shfl_sync(kFull, acc, 0), __shfl_sync(kFull, acc, 1), __shfl_sync(kFull, acc, 2), __shfl_sync(kFull, acc, 3),
                   __shfl_sync(kFull, acc, 4));
@@ -392,40 +408,98 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         stage<C::IR, C::SI, C::NT>(ireg, lvI, imgI, iax, ipy - 1, oi, WW + 3, tid);
         point_sync<WPP>(bar);
 
-        // ---- Scharr derivative at the (WW+1) x (WH+1) integer positions the patch touches -----------------
-        for (int u = tid; u < C::NRUN; u += C::NT) {
-            const int dy = u / C::RPR;
-            const int dx0 = 4 * (u - dy * C::RPR);
-            const uint8_t* r0 = ireg + dy * C::SI + oi + dx0;
-            const uint8_t* r1 = r0 + C::SI;
-            const uint8_t* r2 = r1 + C::SI;
-            int t0[6], t1[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int a = r0[k], b = r1[k], cc = r2[k];
-                t0[k] = 3 * (a + cc) + 10 * b;
-                t1[k] = cc - a;
-            }
-            const bool yin = (unsigned)(ipy + dy) < (unsigned)lh;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int dx = dx0 + k;
-                const int gx = t0[k + 2] - t0[k];
-                const int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
-                const bool in = yin && ((unsigned)(ipx + dx) < (unsigned)lw);
-                if (dx < C::SD) dreg[dy * C::SD + dx] = in ? (((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16)) : 0u;
-            }
-        }
-        point_sync<WPP>(bar);
-
-        // ---- patch pass: per-thread register patch + integer class sums of G ------------------------------
+        // ---- patch pass: Q5 intensity + Q14 derivative patch into registers, integer class sums of G ------------
         const uint32_t W0 = (uint32_t)(w00 & 0xffff) | ((uint32_t)w01 << 16);
         const uint32_t W1 = (uint32_t)(w10 & 0xffff) | ((uint32_t)w11 << 16);
         PxStore<C::PACK> pxs[C::UPT][4];
         int vals[16];
-        {
-            unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, t11 = 0, t22 = 0;
-            int q12[4] = {0, 0, 0, 0}, t12 = 0;
+        unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, t11 = 0, t22 = 0;
+        int q12[4] = {0, 0, 0, 0}, t12 = 0;
+        // all (WW+1) x (WH+1) derivative positions inside the image <=> no zero-masking of the derivative
+        const bool interior = (ipx >= 0) && (ipy >= 0) && (ipx + WW < lw) && (ipy + WH < lh);
+        if (interior) {
+            // Scharr is linear and so is the Q14 bilinear tap, so  sum_c w_c * Scharr(I)(p + c)  ==  Scharr(T)(p)  with
+            // T(q) = sum_c w_c * I(q + c) the UNROUNDED bilinear sum (<= 255 * 2^14); exact in int32 (|.| < 2^27).
+            const int sh = (oi & 3) * 8;
+#pragma unroll
+            for (int k = 0; k < C::UPT; ++k) {
+                const int y = unit_y(k), x0 = unit_x0(k);
+                const bool ok = unit_ok(k);
+                uint32_t pa[4], pb[4], pc[4], pd[4];   // byte pairs (c,c+1) of 4 region rows: see pair() below
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ireg + (y + r) * C::SI) + ((oi + x0) >> 2);
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                    pa[r] = __funnelshift_r(w0, w1, sh);        // bytes c0 .. c0+3   (c0 = column of window x0-1)
+                    pb[r] = __funnelshift_rc(w0, w1, sh + 8);   // bytes c0+1 .. c0+4
+                    pc[r] = __funnelshift_r(w1, w2, sh);        // bytes c0+4 .. c0+7
+                    pd[r] = __funnelshift_rc(w1, w2, sh + 8);   // bytes c0+5 .. c0+8
+                }
+                int T[3][6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    T[r][0] = dp2a_lo(W1, pa[r + 1], dp2a_lo(W0, pa[r], 0));
+                    T[r][1] = dp2a_lo(W1, pb[r + 1], dp2a_lo(W0, pb[r], 0));
+                    T[r][2] = dp2a_hi(W1, pa[r + 1], dp2a_hi(W0, pa[r], 0));
+                    T[r][3] = dp2a_hi(W1, pb[r + 1], dp2a_hi(W0, pb[r], 0));
+                    T[r][4] = dp2a_lo(W1, pc[r + 1], dp2a_lo(W0, pc[r], 0));
+                    T[r][5] = dp2a_lo(W1, pd[r + 1], dp2a_lo(W0, pd[r], 0));
+                }
+                int t0[6], t1[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    t0[c] = 3 * (T[0][c] + T[2][c]) + 10 * T[1][c];
+                    t1[c] = T[2][c] - T[0][c];
+                }
+                unsigned u11[4], u22[4];
+                int u12[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool valid = ok && (x0 + j) < WW;
+                    const int iv = (T[1][j + 1] + (1 << 8)) >> 9;
+                    int gx = (t0[j + 2] - t0[j] + (1 << 13)) >> 14;
+                    int gy = (3 * (t1[j] + t1[j + 2]) + 10 * t1[j + 1] + (1 << 13)) >> 14;
+                    gx = valid ? gx : 0; gy = valid ? gy : 0;
+                    pxs[k][j].set(valid ? iv : 0, gx, gy, max(abs(gx), abs(gy)));
+                    u11[j] = (unsigned)(gx * gx); u12[j] = gx * gy; u22[j] = (unsigned)(gy * gy);
+                }
+                const bool tail = x0 >= C::NV;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    q11[j] += tail ? 0u : u11[j];
+                    q12[j] += tail ? 0 : u12[j];
+                    q22[j] += tail ? 0u : u22[j];
+                }
+                t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
+                t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
+                t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
+            }
+        } else {
+            // border window: Scharr at the (WW+1) x (WH+1) integer positions, zero outside the image, then bilinear
+            for (int u = tid; u < C::NRUN; u += C::NT) {
+                const int dy = u / C::RPR;
+                const int dx0 = 4 * (u - dy * C::RPR);
+                const uint8_t* r0 = ireg + dy * C::SI + oi + dx0;
+                const uint8_t* r1 = r0 + C::SI;
+                const uint8_t* r2 = r1 + C::SI;
+                int t0[6], t1[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int a = r0[k], b = r1[k], cc = r2[k];
+                    t0[k] = 3 * (a + cc) + 10 * b;
+                    t1[k] = cc - a;
+                }
+                const bool yin = (unsigned)(ipy + dy) < (unsigned)lh;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int dx = dx0 + k;
+                    const int gx = t0[k + 2] - t0[k];
+                    const int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
+                    const bool in = yin && ((unsigned)(ipx + dx) < (unsigned)lw);
+                    if (dx < C::SD) dreg[dy * C::SD + dx] = in ? (((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16)) : 0u;
+                }
+            }
+            point_sync<WPP>(bar);
 #pragma unroll
             for (int k = 0; k < C::UPT; ++k) {
                 const int y = unit_y(k), x0 = unit_x0(k);
@@ -466,6 +540,8 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
                 t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
             }
+        }
+        {
             const unsigned cap = (1u << 25) / WPP;  // keeps the point-wide totals below 2^31
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -478,32 +554,36 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             vals[14] = (int)min(t22, cap);
             vals[15] = 0;
         }
-        point_sum16<WPP>(vals, red16, par16, wip, lane, bar);
+        // lane L < 15 now holds class total L: [0..4] = gx*gx (4 SIMD lanes, tail), [5..9] = gx*gy, [10..14] = gy*gy
+        const int gtot = point_sum15_lane<WPP>(vals, red16, par16, wip, lane, bar);
 
         float A11, A12, A22;
         {
             // A11 / A22: non-negative terms, exact iff every class total <= 2^24; A12: |gx gy| <= (gx^2 + gy^2) / 2
-            bool exact = true;
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                exact = exact && ((unsigned)vals[k] <= (unsigned)kExact) && ((unsigned)vals[10 + k] <= (unsigned)kExact) &&
-                        ((unsigned)vals[k] + (unsigned)vals[10 + k] <= 2u * (unsigned)kExact);
-            if (exact) {
-                A11 = combine5((float)vals[0], (float)vals[1], (float)vals[2], (float)vals[3], (float)vals[4]);
-                A12 = combine5((float)vals[5], (float)vals[6], (float)vals[7], (float)vals[8], (float)vals[9]);
-                A22 = combine5((float)vals[10], (float)vals[11], (float)vals[12], (float)vals[13], (float)vals[14]);
+            const unsigned partner = (unsigned)__shfl_sync(kFull, gtot, (lane + 10) & 31);
+            const bool ok = (lane >= 5) || ((unsigned)gtot <= (unsigned)kExact && partner <= (unsigned)kExact &&
+                                            (unsigned)gtot + partner <= 2u * (unsigned)kExact);
+            if (__all_sync(kFull, ok)) {
+                const float f = (float)gtot;
+                A11 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
+                               __shfl_sync(kFull, f, 4));
+                A12 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
+                               __shfl_sync(kFull, f, 9));
+                A22 = combine5(__shfl_sync(kFull, f, 10), __shfl_sync(kFull, f, 11), __shfl_sync(kFull, f, 12), __shfl_sync(kFull, f, 13),
+                               __shfl_sync(kFull, f, 14));
             } else {
                 // serial replay in OpenCV's order (A.5) from a chain-ordered smem copy of the derivative patch
-                uint32_t* dpat = dreg;  // dreg is dead (everyone passed the point_sum16 barrier)
+                uint32_t* dpat = dreg;  // dreg is dead (every warp passed the exchange barrier above)
 #pragma unroll
                 for (int k = 0; k < C::UPT; ++k)
                     if (unit_ok(k)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (unit_x0(k) + j < WW)
-                                dpat[chain_slot_g<WW, WH>(unit_y(k), unit_x0(k) + j)] =
+                                dpat[Chains<WW, WH>::slot_g(unit_y(k), unit_x0(k) + j)] =
                                     ((uint32_t)pxs[k][j].gx() & 0xffffu) | ((uint32_t)pxs[k][j].gy() << 16);
                     }
+                zero_pad_g<WW, WH, C::NT>(dpat, tid);
                 point_sync<WPP>(bar);
                 replay_g<WW, WH>(dpat, lane, A11, A12, A22);  // every warp of the point computes the same values
             }
@@ -531,6 +611,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         };
 
         float pdx = 0.f, pdy = 0.f;
+        bool sticky = false, pads_zeroed = false;
         for (int j = 0; j < L.max_count; ++j) {
             int inx, iny;
             if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
@@ -573,16 +654,25 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     }
                 }
             }
-            // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 16; clamp so the point total cannot wrap
-            bnd = min(bnd, (1 << 25) / WPP);
-            point_sum3<WPP>(s1, s2, bnd, red3, par3, wip, lane, bar);
-            float b1, b2;
-            if (bnd <= kExact) {
-                // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
-                b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
-                b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
-            } else {
-                // tier 1: per accumulation class
+            // Tier 0 (whole-window bound) unless the previous iteration of this point already failed it ("sticky"):
+            // diverging points fail it every time, and they are the ones that bound the launch latency.
+            float b1 = 0.f, b2 = 0.f;
+            bool classes = sticky;
+            if (!sticky) {
+                // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamp so the point total cannot wrap
+                bnd = min(bnd, (1 << 25) / WPP);
+                point_sum3<WPP>(s1, s2, bnd, red3, par3, wip, lane, bar);
+                if (bnd <= kExact) {
+                    // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
+                    b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
+                    b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
+                } else {
+                    sticky = true;
+                    classes = true;
+                }
+            }
+            if (classes) {
+                // tier 1: per accumulation class (4 SIMD lanes + tail), bound in units of 16 (rounded up per pixel)
                 ++n_t1;
                 int cv[16];
 #pragma unroll
@@ -610,13 +700,17 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 }
 #pragma unroll
                 for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (1 << 22) / WPP);
-                point_sum16<WPP>(cv, red16, par16, wip, lane, bar);
-                bool exact = true;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) exact = exact && (cv[10 + k] <= (kExact >> 4));
+                const int ctot = point_sum15_lane<WPP>(cv, red16, par16, wip, lane, bar);
+                const bool is_bound = (lane >= 10) && (lane < 15);
+                const bool exact = __all_sync(kFull, !is_bound || ctot <= (kExact >> 4));
+                // leave sticky mode once the whole-window bound would pass again (converging point)
+                sticky = __reduce_add_sync(kFull, is_bound ? ctot : 0) > (kExact >> 4);
                 if (exact) {
-                    b1 = combine5((float)cv[0], (float)cv[1], (float)cv[2], (float)cv[3], (float)cv[4]);
-                    b2 = combine5((float)cv[5], (float)cv[6], (float)cv[7], (float)cv[8], (float)cv[9]);
+                    const float f = (float)ctot;
+                    b1 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
+                                  __shfl_sync(kFull, f, 4));
+                    b2 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
+                                  __shfl_sync(kFull, f, 9));
                 } else {
                     // tier 2: serial replay (pairs (l, l+4) summed in int32 first; A.5)
                     ++n_t2;
@@ -627,12 +721,13 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
                                 if (unit_x0(k) + jj < WW) {
-                                    const int slot = chain_slot_b<WW, WH>(unit_y(k), unit_x0(k) + jj);
+                                    const int slot = Chains<WW, WH>::slot_b(unit_y(k), unit_x0(k) + jj);
                                     const int d = dd[k].get(jj);
                                     prod[slot] = d * pxs[k][jj].gx();
-                                    prod[WW * WH + slot] = d * pxs[k][jj].gy();
+                                    prod[5 * Chains<WW, WH>::BLEN + slot] = d * pxs[k][jj].gy();
                                 }
                         }
+                    if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(prod, tid); pads_zeroed = true; }  // pads survive until the next level
                     point_sync<WPP>(bar);
                     replay_b<WW, WH>(prod, lane, b1, b2);  // every warp of the point computes the same values
                     point_sync<WPP>(bar);  // scratch is rewritten by the next replay only after everyone is here

@@ -7,9 +7,13 @@
 //
 // Design (HBM-bound byte work, no tensor cores):
 //  * one warp owns a strip of 64*NOUT input columns x (2R+3) input rows and produces 32*NOUT x R
-//    outputs; each lane loads its own 2*NOUT contiguous bytes per input row with ONE 64/128-bit
-//    coalesced load and gets the 2+1 halo columns from its neighbours by warp shuffle (register
-//    halo staging -- no shared-memory round trip, every input byte crosses the LSU once);
+//    outputs.  Main kernel (16-byte aligned rows): every lane streams its 2*NOUT contiguous bytes of
+//    each input row into a per-warp shared-memory ring with ONE 128/64-bit cp.async (LDGSTS: no
+//    registers held while in flight, 4 rows = 2 KB per warp of lookahead, no block-level barriers);
+//    the 2+1 halo columns are the neighbouring lanes' bytes in the same ring slot, so the consumer
+//    reads them with plain LDS -- REFLECT_101 at the image edges is patched in the slot (2 byte
+//    copies per row, edge warps only).  Fallback kernel (unaligned pitches / tiny images): direct
+//    loads + warp shuffles + byte gathers.
 //  * bytes are widened to packed u16x2 lanes (PRMT) so one 32-bit op filters two columns; the
 //    vertical pass is a sliding window (T_y = r[2y] + 4 r[2y+1] + r[2y+2]; V_y = T_{y-1} + T_y +
 //    4 r[2y]) so each input row is loaded and unpacked once per strip; the horizontal pass works
@@ -18,6 +22,8 @@
 //  * image borders (REFLECT_101) and unaligned pitches take a byte-gather path in the edge lanes
 //    only; interior lanes never branch on coordinates.
 #include "klt_common.cuh"
+
+#include <cstdlib>
 
 namespace klt {
 
@@ -182,6 +188,213 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Main kernel: cp.async ring.  Requires 16-byte aligned src rows, 8-byte aligned dst rows, w >= 3.
+constexpr int kRing = 8;  // ring slots (input rows) per warp
+
+template <int NOUT>
+struct RingCfg {
+    static constexpr int BODY = 64 * NOUT;              // bytes of one input row owned by the warp
+    static constexpr int SLOT = BODY + 32;              // [12 pad][4 left halo][BODY][4 right halo][12 pad]
+    static constexpr int WARP_BYTES = kRing * SLOT;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NOUT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
+                     uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                     int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+{
+    using RC = RingCfg<NOUT>;
+    constexpr int NW = NOUT / 2;
+    constexpr int NP = NOUT + 3;
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+
+    const int tx = (int)(task % tiles_x);
+    const long long t2 = task / tiles_x;
+    const int sy = (int)(t2 % strips_y);
+    const int b = (int)(t2 / strips_y);
+    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
+    uint8_t* __restrict__ dimg = dst + (long long)b * dbatch;
+
+    uint8_t* ring = ring_smem + warp * RC::WARP_BYTES;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const int X0 = tx * RC::BODY;                 // first input column of the tile
+    const int cb = X0 + 2 * NOUT * lane;          // first own input column
+    const int own_bytes = max(0, min(2 * NOUT, w - cb));
+    const int y0 = sy * rows_per_strip;
+    const int y1 = min(y0 + rows_per_strip, dh);
+    const int n_rows = 2 * (y1 - y0) + 3;         // input rows 2*y0-2 .. 2*y1
+
+    // issue input row i (image row 2*y0 - 2 + i, reflected) into slot i % kRing; always one commit group
+    auto issue = [&](int i) {
+        if (i < n_rows) {
+            const uint8_t* __restrict__ row = simg + (long long)reflect101(2 * y0 - 2 + i, h) * spitch;
+            const uint32_t slot = ring_s + (uint32_t)((i & (kRing - 1)) * RC::SLOT);
+            if (own_bytes > 0) {
+                if constexpr (NOUT == 8) cp_async_16(slot + 16 + 16 * lane, row + cb, own_bytes);
+                else cp_async_8(slot + 16 + 8 * lane, row + cb, own_bytes);
+            }
+            if (lane == 0 && X0 > 0) cp_async_4(slot + 12, row + X0 - 4, 4);
+            if (lane == 31) {
+                const int rb = max(0, min(4, w - (X0 + RC::BODY)));
+                if (rb > 0) cp_async_4(slot + 16 + RC::BODY, row + X0 + RC::BODY, rb);
+            }
+        }
+        cp_async_commit();
+    };
+    // REFLECT_101 columns -2,-1 (left image edge) and w, w+1 (right edge) patched inside the landed slot
+    const bool fix_left = (X0 == 0);
+    const bool fix_right = (w + 1 >= X0 - 4) && (w < X0 + RC::BODY + 4);
+    auto fixup = [&](int i) {
+        uint8_t* sl = ring + (i & (kRing - 1)) * RC::SLOT + 16;   // sl[c] = column X0 + c
+        if (fix_left && lane == 0) { sl[-2] = sl[2]; sl[-1] = sl[1]; }
+        if (fix_right && lane == 1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = w + k - X0, sc = w - 2 - k - X0;   // column w+k mirrors column w-2-k
+                if (c >= -4 && c < RC::BODY + 4 && sc >= -4) sl[c] = sl[sc];
+            }
+        }
+    };
+    auto load_row = [&](int i, uint32_t (&p)[NP]) {
+        const uint8_t* sl = ring + (i & (kRing - 1)) * RC::SLOT + 16 + 2 * NOUT * lane;
+        const uint32_t l = *reinterpret_cast<const uint32_t*>(sl - 4);
+        const uint32_t r = *reinterpret_cast<const uint32_t*>(sl + 2 * NOUT);
+        uint32_t wv[NW];
+        if constexpr (NOUT == 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sl);
+            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+        } else {
+            const uint2 v = *reinterpret_cast<const uint2*>(sl);
+            wv[0] = v.x; wv[1] = v.y;
+        }
+        p[0] = even_bytes(l);
+        p[1] = odd_bytes(l);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            p[2 + 2 * k] = even_bytes(wv[k]);
+            p[3 + 2 * k] = odd_bytes(wv[k]);
+        }
+        p[NOUT + 2] = even_bytes(r);
+    };
+
+#pragma unroll
+    for (int i = 0; i < 7; ++i) issue(i);
+    cp_async_wait<4>();   // rows 0, 1, 2 have landed
+    __syncwarp();
+    if (fix_left || fix_right) {
+        fixup(0); fixup(1); fixup(2);
+        __syncwarp();
+    }
+    uint32_t tprev[NP], rc[NP];
+    {
+        uint32_t pa[NP], pb[NP];
+        load_row(0, pa);
+        load_row(1, pb);
+        load_row(2, rc);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) tprev[i] = pa[i] + 4u * pb[i] + rc[i];
+    }
+    const int xo = cb >> 1;
+    for (int y = y0, t = 0; y < y1; ++y, ++t) {
+        cp_async_wait<2>();   // rows <= 2t+4 have landed (the two newest groups may still be in flight)
+        __syncwarp();
+        if (fix_left || fix_right) {
+            fixup(2 * t + 3); fixup(2 * t + 4);
+            __syncwarp();
+        }
+        uint32_t ro[NP], re[NP];
+        load_row(2 * t + 3, ro);
+        load_row(2 * t + 4, re);
+        issue(2 * t + 7);     // slots of rows 2t-1, 2t: last read two iterations ago
+        issue(2 * t + 8);
+        uint32_t v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const uint32_t tt = rc[i] + 4u * ro[i] + re[i];
+            v[i] = tprev[i] + tt + 4u * rc[i];
+            tprev[i] = tt;
+            rc[i] = re[i];
+        }
+        uint32_t s[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t e_m = v[2 * i], o_m = v[2 * i + 1];
+            const uint32_t e_c = v[2 * i + 2], o_c = v[2 * i + 3];
+            const uint32_t e_p = v[2 * i + 4];
+            const uint32_t a = __funnelshift_r(e_m, e_c, 16);
+            const uint32_t c = __funnelshift_r(e_c, e_p, 16);
+            const uint32_t oa = __funnelshift_r(o_m, o_c, 16);
+            s[i] = a + c + 6u * e_c + 4u * (oa + o_c) + 0x00800080u;
+        }
+        uint8_t* drow = dimg + (long long)y * dpitch + xo;
+        if (xo + NOUT <= dw) {
+            if constexpr (NOUT == 8) {
+                uint2 o;
+                o.x = prmt(s[0], s[1], 0x7531u);
+                o.y = prmt(s[2], s[3], 0x7531u);
+                *reinterpret_cast<uint2*>(drow) = o;
+            } else {
+                *reinterpret_cast<uint32_t*>(drow) = prmt(s[0], s[1], 0x7531u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                if (xo + 2 * i < dw) drow[2 * i] = (uint8_t)(s[i] >> 8);
+                if (xo + 2 * i + 1 < dw) drow[2 * i + 1] = (uint8_t)(s[i] >> 24);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <int NOUT>
+klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+{
+    using RC = RingCfg<NOUT>;
+    static bool configured = false;
+    const int smem = RC::WARP_BYTES * kWarpsPerBlock;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (klt_status)e;
+        configured = true;
+    }
+    const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
+    int rows = 16;
+    const long long want = (long long)sm_count * kWarpsPerBlock * 4;
+    while (rows > 2 && (long long)tiles_x * ((dh + rows - 1) / rows) * batch < want) rows >>= 1;
+    const int strips_y = (dh + rows - 1) / rows;
+    const long long n_tasks = (long long)tiles_x * strips_y * batch;
+    const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    pyr_down_ring_kernel<NOUT><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
 template <int NOUT, bool ALIGNED>
 klt_status launch_t(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
                     int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count,
@@ -216,6 +429,11 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
     // 8 outputs per lane (128-bit loads) unless the 256-wide warp tile would waste > 1/4 of its lanes
     const int t8 = (dw + 255) / 256 * 256, t4 = (dw + 127) / 128 * 128;
     const bool use8 = (t8 * 3 <= dw * 4) || (t8 == t4);
+    static const char* force_fallback = getenv("KLT_PYR_FALLBACK");   // tests: exercise the shuffle/gather kernel
+    if (aligned && w >= 3 && !(force_fallback && force_fallback[0] == '1')) {
+        return use8 ? launch_ring<8>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
+                    : launch_ring<4>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+    }
     if (aligned) {
         return use8 ? launch_t<8, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
                     : launch_t<4, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
