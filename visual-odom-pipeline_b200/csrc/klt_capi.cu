@@ -1,7 +1,9 @@
 // C ABI of libklt_b200.so (see include/klt_b200.h): context, pyramid planning, kernel launches
 // and the host-pointer entry points that stand in for cv2.calcOpticalFlowPyrLK /
 // cv2.buildOpticalFlowPyramid as called from reference src/extractor/extractor.py:44,45,65,66.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -293,6 +295,12 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     if (s != KLT_OK) return s;
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream;
+    static const bool trace = getenv("KLT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
     KLT_CUDA(cudaMemcpy2DAsync(d + off_img, ipitch, prev_img, (size_t)prev_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
     KLT_CUDA(cudaMemcpy2DAsync(d + off_img + ibytes, ipitch, next_img, (size_t)next_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
     float* d_next = reinterpret_cast<float*>(d + off_out);
@@ -301,6 +309,9 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)
         KLT_CUDA(cudaMemcpyAsync(d_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const auto t1 = now();
+    if (trace) { cudaStreamSynchronize(st); }
+    const auto t1s = now();
     s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, 0, 0, st);
     if (s != KLT_OK) return s;
     // the pair lives in one batch-2 pyramid: prev = item 0, next = item 1
@@ -316,8 +327,15 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     L.min_eig_thr = (float)params->min_eig_threshold;
     s = lk_launch(L, ctx->sm_count, st);
     if (s != KLT_OK) return s;
+    const auto t2 = now();
+    if (trace) { cudaStreamSynchronize(st); }
+    const auto t2s = now();
     KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d + off_out, out_bytes, cudaMemcpyDeviceToHost, st));
     KLT_CUDA(cudaStreamSynchronize(st));
+    const auto t3 = now();
+    if (trace)
+        std::fprintf(stderr, "[klt trace] h2d enqueue %.1f us, h2d done +%.1f us, kernels enqueue %.1f us, kernels done +%.1f us, d2h+sync %.1f us\n",
+                     us(t0, t1), us(t1, t1s), us(t1s, t2), us(t2, t2s), us(t2s, t3));
     std::memcpy(next_pts, ctx->h_ws, (size_t)n * 8);
     std::memcpy(err, ctx->h_ws + (size_t)n * 8, (size_t)n * 4);
     std::memcpy(status, ctx->h_ws + (size_t)n * 12, (size_t)n);

@@ -215,8 +215,34 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 template <int NOUT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
                      uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
                      int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
@@ -235,138 +261,167 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
     const int sy = (int)(t2 % strips_y);
     const int b = (int)(t2 / strips_y);
     const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
-    uint8_t* __restrict__ dimg = dst + (long long)b * dbatch;
 
-    uint8_t* ring = ring_smem + warp * RC::WARP_BYTES;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RC::WARP_BYTES);
     const int X0 = tx * RC::BODY;                 // first input column of the tile
     const int cb = X0 + 2 * NOUT * lane;          // first own input column
     const int own_bytes = max(0, min(2 * NOUT, w - cb));
     const int y0 = sy * rows_per_strip;
     const int y1 = min(y0 + rows_per_strip, dh);
     const int n_rows = 2 * (y1 - y0) + 3;         // input rows 2*y0-2 .. 2*y1
+    const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
+    const uint8_t* __restrict__ gown = simg + cb;
+    // one extra 4-byte halo copy per row: lane 0 fetches columns X0-4..X0-1, lane 31 columns X0+BODY..X0+BODY+3
+    const int rb = max(0, min(4, w - (X0 + RC::BODY)));
+    const bool has_x = (lane == 0 && X0 > 0) || (lane == 31 && rb > 0);
+    const int x_bytes = (lane == 0) ? 4 : rb;
+    const uint32_t x_s = ring_s + ((lane == 0) ? 12u : (uint32_t)(16 + RC::BODY));
+    const uint8_t* __restrict__ gx = simg + ((lane == 0) ? (X0 - 4) : (X0 + RC::BODY));
+    const int hm2 = 2 * h - 2;
+    const unsigned pitch32 = (unsigned)spitch;   // h * pitch < 2^31 is checked by the launcher
 
-    // issue input row i (image row 2*y0 - 2 + i, reflected) into slot i % kRing; always one commit group
-    auto issue = [&](int i) {
-        if (i < n_rows) {
-            const uint8_t* __restrict__ row = simg + (long long)reflect101(2 * y0 - 2 + i, h) * spitch;
-            const uint32_t slot = ring_s + (uint32_t)((i & (kRing - 1)) * RC::SLOT);
-            if (own_bytes > 0) {
-                if constexpr (NOUT == 8) cp_async_16(slot + 16 + 16 * lane, row + cb, own_bytes);
-                else cp_async_8(slot + 16 + 8 * lane, row + cb, own_bytes);
-            }
-            if (lane == 0 && X0 > 0) cp_async_4(slot + 12, row + X0 - 4, 4);
-            if (lane == 31) {
-                const int rb = max(0, min(4, w - (X0 + RC::BODY)));
-                if (rb > 0) cp_async_4(slot + 16 + RC::BODY, row + X0 + RC::BODY, rb);
-            }
-        }
-        cp_async_commit();
-    };
-    // REFLECT_101 columns -2,-1 (left image edge) and w, w+1 (right edge) patched inside the landed slot
-    const bool fix_left = (X0 == 0);
-    const bool fix_right = (w + 1 >= X0 - 4) && (w < X0 + RC::BODY + 4);
-    auto fixup = [&](int i) {
-        uint8_t* sl = ring + (i & (kRing - 1)) * RC::SLOT + 16;   // sl[c] = column X0 + c
-        if (fix_left && lane == 0) { sl[-2] = sl[2]; sl[-1] = sl[1]; }
-        if (fix_right && lane == 1) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int c = w + k - X0, sc = w - 2 - k - X0;   // column w+k mirrors column w-2-k
-                if (c >= -4 && c < RC::BODY + 4 && sc >= -4) sl[c] = sl[sc];
-            }
-        }
-    };
-    auto load_row = [&](int i, uint32_t (&p)[NP]) {
-        const uint8_t* sl = ring + (i & (kRing - 1)) * RC::SLOT + 16 + 2 * NOUT * lane;
-        const uint32_t l = *reinterpret_cast<const uint32_t*>(sl - 4);
-        const uint32_t r = *reinterpret_cast<const uint32_t*>(sl + 2 * NOUT);
-        uint32_t wv[NW];
-        if constexpr (NOUT == 8) {
-            const uint4 v = *reinterpret_cast<const uint4*>(sl);
-            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
-        } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(sl);
-            wv[0] = v.x; wv[1] = v.y;
-        }
-        p[0] = even_bytes(l);
-        p[1] = odd_bytes(l);
-#pragma unroll
-        for (int k = 0; k < NW; ++k) {
-            p[2 + 2 * k] = even_bytes(wv[k]);
-            p[3 + 2 * k] = odd_bytes(wv[k]);
-        }
-        p[NOUT + 2] = even_bytes(r);
-    };
+    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (h >= 3: one reflection is enough);
+    // SO_ = compile-time ring slot offset
+#define KLT_ISSUE(i_, SO_)                                                                              \
+    do {                                                                                                \
+        if ((i_) < n_rows) {                                                                            \
+            int r_ = 2 * y0 - 2 + (i_);                                                                 \
+            r_ = r_ < 0 ? -r_ : r_;                                                                     \
+            r_ = r_ >= h ? hm2 - r_ : r_;                                                               \
+            const unsigned off_ = (unsigned)r_ * pitch32;                                               \
+            if (own_bytes > 0) {                                                                        \
+                if constexpr (NOUT == 8) cp_async_16(my_s + (SO_), gown + off_, own_bytes);             \
+                else cp_async_8(my_s + (SO_), gown + off_, own_bytes);                                  \
+            }                                                                                           \
+            if (has_x) cp_async_4(x_s + (SO_), gx + off_, x_bytes);                                     \
+        }                                                                                               \
+        cp_async_commit();                                                                              \
+    } while (0)
 
-#pragma unroll
-    for (int i = 0; i < 7; ++i) issue(i);
+    // REFLECT_101 at the right image edge: columns w, w+1 mirror w-2, w-3; patched inside the landed slot by two
+    // lanes (the sources are always inside the slot: body or left halo).  The left edge is fixed in registers.
+    const bool fix_right = (w < X0 + RC::BODY + 4);
+    const int fr_c = w - X0 + lane;                  // lane 0: column w (mirror: -2), lane 1: column w+1 (mirror: -4)
+    const bool fr_on = (lane < 2) && (fr_c < RC::BODY + 4);
+    const uint32_t fr_dst = ring_s + 16 + fr_c, fr_src = fr_dst - 2 - 2 * lane;
+#define KLT_FIX_RIGHT(SO_)                                                                              \
+    do {                                                                                                \
+        if (fr_on) sts_u8(fr_dst + (SO_), lds_u8(fr_src + (SO_)));                                      \
+    } while (0)
+
+    const bool fix_left = (X0 == 0) && (lane == 0);
+#define KLT_LOAD_ROW(SO_, p_)                                                                           \
+    do {                                                                                                \
+        const uint32_t a_ = my_s + (SO_);                                                               \
+        uint32_t wv_[NW];                                                                               \
+        if constexpr (NOUT == 8) {                                                                      \
+            const uint4 v_ = lds_v4(a_);                                                                \
+            wv_[0] = v_.x; wv_[1] = v_.y; wv_[2] = v_.z; wv_[3] = v_.w;                                 \
+        } else {                                                                                        \
+            const uint2 v_ = lds_v2(a_);                                                                \
+            wv_[0] = v_.x; wv_[1] = v_.y;                                                               \
+        }                                                                                               \
+        uint32_t l_ = lds_u32(a_ - 4);                                                                  \
+        const uint32_t r_ = lds_u32(a_ + 2 * NOUT);                                                     \
+        if (fix_left) l_ = prmt(wv_[0], wv_[0], 0x1200u); /* columns -2,-1 mirror 2,1 */                \
+        (p_)[0] = even_bytes(l_);                                                                       \
+        (p_)[1] = odd_bytes(l_);                                                                        \
+        _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                             \
+            (p_)[2 + 2 * k_] = even_bytes(wv_[k_]);                                                     \
+            (p_)[3 + 2 * k_] = odd_bytes(wv_[k_]);                                                      \
+        }                                                                                               \
+        (p_)[NOUT + 2] = even_bytes(r_);                                                                \
+    } while (0)
+#define KLT_SLOT(i_) ((uint32_t)((((i_) % kRing + kRing) % kRing) * RC::SLOT))
+
+    KLT_ISSUE(0, KLT_SLOT(0)); KLT_ISSUE(1, KLT_SLOT(1)); KLT_ISSUE(2, KLT_SLOT(2)); KLT_ISSUE(3, KLT_SLOT(3));
+    KLT_ISSUE(4, KLT_SLOT(4)); KLT_ISSUE(5, KLT_SLOT(5)); KLT_ISSUE(6, KLT_SLOT(6));
     cp_async_wait<4>();   // rows 0, 1, 2 have landed
     __syncwarp();
-    if (fix_left || fix_right) {
-        fixup(0); fixup(1); fixup(2);
+    if (fix_right) {      // warp-uniform
+        KLT_FIX_RIGHT(KLT_SLOT(0)); KLT_FIX_RIGHT(KLT_SLOT(1)); KLT_FIX_RIGHT(KLT_SLOT(2));
         __syncwarp();
     }
     uint32_t tprev[NP], rc[NP];
     {
         uint32_t pa[NP], pb[NP];
-        load_row(0, pa);
-        load_row(1, pb);
-        load_row(2, rc);
+        KLT_LOAD_ROW(KLT_SLOT(0), pa);
+        KLT_LOAD_ROW(KLT_SLOT(1), pb);
+        KLT_LOAD_ROW(KLT_SLOT(2), rc);
 #pragma unroll
         for (int i = 0; i < NP; ++i) tprev[i] = pa[i] + 4u * pb[i] + rc[i];
     }
     const int xo = cb >> 1;
-    for (int y = y0, t = 0; y < y1; ++y, ++t) {
-        cp_async_wait<2>();   // rows <= 2t+4 have landed (the two newest groups may still be in flight)
-        __syncwarp();
-        if (fix_left || fix_right) {
-            fixup(2 * t + 3); fixup(2 * t + 4);
-            __syncwarp();
-        }
-        uint32_t ro[NP], re[NP];
-        load_row(2 * t + 3, ro);
-        load_row(2 * t + 4, re);
-        issue(2 * t + 7);     // slots of rows 2t-1, 2t: last read two iterations ago
-        issue(2 * t + 8);
-        uint32_t v[NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const uint32_t tt = rc[i] + 4u * ro[i] + re[i];
-            v[i] = tprev[i] + tt + 4u * rc[i];
-            tprev[i] = tt;
-            rc[i] = re[i];
-        }
-        uint32_t s[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t e_m = v[2 * i], o_m = v[2 * i + 1];
-            const uint32_t e_c = v[2 * i + 2], o_c = v[2 * i + 3];
-            const uint32_t e_p = v[2 * i + 4];
-            const uint32_t a = __funnelshift_r(e_m, e_c, 16);
-            const uint32_t c = __funnelshift_r(e_c, e_p, 16);
-            const uint32_t oa = __funnelshift_r(o_m, o_c, 16);
-            s[i] = a + c + 6u * e_c + 4u * (oa + o_c) + 0x00800080u;
-        }
-        uint8_t* drow = dimg + (long long)y * dpitch + xo;
-        if (xo + NOUT <= dw) {
-            if constexpr (NOUT == 8) {
-                uint2 o;
-                o.x = prmt(s[0], s[1], 0x7531u);
-                o.y = prmt(s[2], s[3], 0x7531u);
-                *reinterpret_cast<uint2*>(drow) = o;
-            } else {
-                *reinterpret_cast<uint32_t*>(drow) = prmt(s[0], s[1], 0x7531u);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                if (xo + 2 * i < dw) drow[2 * i] = (uint8_t)(s[i] >> 8);
-                if (xo + 2 * i + 1 < dw) drow[2 * i + 1] = (uint8_t)(s[i] >> 24);
-            }
-        }
+    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
+    const bool full_store = (xo + NOUT <= dw);
+    const int n_out = y1 - y0;
+
+    // one output row; K_ = t % 4 fixes every ring slot offset at compile time (rows 2t+3, 2t+4 are consumed, rows
+    // 2t+7, 2t+8 are issued into the slots of rows 2t-1, 2t, last read two iterations ago)
+#define KLT_STEP(K_)                                                                                    \
+    do {                                                                                                \
+        cp_async_wait<2>(); /* rows <= 2t+4 have landed; the two newest groups may still be in flight */ \
+        __syncwarp();                                                                                   \
+        if (fix_right) {                                                                                \
+            KLT_FIX_RIGHT(KLT_SLOT(2 * (K_) + 3)); KLT_FIX_RIGHT(KLT_SLOT(2 * (K_) + 4));               \
+            __syncwarp();                                                                               \
+        }                                                                                               \
+        uint32_t ro[NP], re[NP];                                                                        \
+        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 3), ro);                                                       \
+        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 4), re);                                                       \
+        KLT_ISSUE(2 * t + 7, KLT_SLOT(2 * (K_) + 7));                                                   \
+        KLT_ISSUE(2 * t + 8, KLT_SLOT(2 * (K_) + 8));                                                   \
+        uint32_t v[NP];                                                                                 \
+        _Pragma("unroll") for (int i = 0; i < NP; ++i) {                                                \
+            const uint32_t tt = rc[i] + 4u * ro[i] + re[i];                                             \
+            v[i] = tprev[i] + tt + 4u * rc[i];                                                          \
+            tprev[i] = tt;                                                                              \
+            rc[i] = re[i];                                                                              \
+        }                                                                                               \
+        uint32_t s_[NW];                                                                                \
+        _Pragma("unroll") for (int i = 0; i < NW; ++i) {                                                \
+            const uint32_t e_m = v[2 * i], o_m = v[2 * i + 1];                                          \
+            const uint32_t e_c = v[2 * i + 2], o_c = v[2 * i + 3];                                      \
+            const uint32_t e_p = v[2 * i + 4];                                                          \
+            const uint32_t a = __funnelshift_r(e_m, e_c, 16);                                           \
+            const uint32_t c = __funnelshift_r(e_c, e_p, 16);                                           \
+            const uint32_t oa = __funnelshift_r(o_m, o_c, 16);                                          \
+            s_[i] = a + c + 6u * e_c + 4u * (oa + o_c) + 0x00800080u;                                   \
+        }                                                                                               \
+        if (full_store) {                                                                               \
+            if constexpr (NOUT == 8) {                                                                  \
+                uint2 o;                                                                                \
+                o.x = prmt(s_[0], s_[1], 0x7531u);                                                      \
+                o.y = prmt(s_[2], s_[NW - 1], 0x7531u);                                                 \
+                *reinterpret_cast<uint2*>(drow) = o;                                                    \
+            } else {                                                                                    \
+                *reinterpret_cast<uint32_t*>(drow) = prmt(s_[0], s_[1], 0x7531u);                       \
+            }                                                                                           \
+        } else {                                                                                        \
+            _Pragma("unroll") for (int i = 0; i < NW; ++i) {                                            \
+                if (xo + 2 * i < dw) drow[2 * i] = (uint8_t)(s_[i] >> 8);                               \
+                if (xo + 2 * i + 1 < dw) drow[2 * i + 1] = (uint8_t)(s_[i] >> 24);                      \
+            }                                                                                           \
+        }                                                                                               \
+        drow += dpitch;                                                                                 \
+        ++t;                                                                                            \
+    } while (0)
+
+    for (int t = 0; t < n_out;) {
+        KLT_STEP(0);
+        if (t >= n_out) break;
+        KLT_STEP(1);
+        if (t >= n_out) break;
+        KLT_STEP(2);
+        if (t >= n_out) break;
+        KLT_STEP(3);
     }
     cp_async_wait<0>();
+#undef KLT_STEP
+#undef KLT_SLOT
+#undef KLT_ISSUE
+#undef KLT_FIX_RIGHT
+#undef KLT_LOAD_ROW
 }
 
 template <int NOUT>
@@ -430,7 +485,7 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
     const int t8 = (dw + 255) / 256 * 256, t4 = (dw + 127) / 128 * 128;
     const bool use8 = (t8 * 3 <= dw * 4) || (t8 == t4);
     static const char* force_fallback = getenv("KLT_PYR_FALLBACK");   // tests: exercise the shuffle/gather kernel
-    if (aligned && w >= 3 && !(force_fallback && force_fallback[0] == '1')) {
+    if (aligned && w >= 4 && h >= 3 && (long long)h * spitch < 0x7fffffffLL && !(force_fallback && force_fallback[0] == '1')) {
         return use8 ? launch_ring<8>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
                     : launch_ring<4>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
     }
