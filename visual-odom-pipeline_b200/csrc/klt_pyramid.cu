@@ -280,16 +280,16 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
     const int hm2 = 2 * h - 2;
     const unsigned pitch32 = (unsigned)spitch;   // h * pitch < 2^31 is checked by the launcher
 
-    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (h >= 3: one reflection is enough);
-    // SO_ = compile-time ring slot offset
+    // input row i of the strip = image row 2*y0-2+i under REFLECT_101; for -h < r < 2h-1 that is
+    // min(|r|, 2h-2-|r|), branch-free.  SO_ = compile-time ring slot offset.  One commit group per row, always.
+    const int r_first = 2 * y0 - 2;
+    const bool do_own = own_bytes > 0;
 #define KLT_ISSUE(i_, SO_)                                                                              \
     do {                                                                                                \
-        if ((i_) < n_rows) {                                                                            \
-            int r_ = 2 * y0 - 2 + (i_);                                                                 \
-            r_ = r_ < 0 ? -r_ : r_;                                                                     \
-            r_ = r_ >= h ? hm2 - r_ : r_;                                                               \
-            const unsigned off_ = (unsigned)r_ * pitch32;                                               \
-            if (own_bytes > 0) {                                                                        \
+        if ((i_) < n_rows) { /* warp-uniform */                                                         \
+            const int ra_ = abs(r_first + (i_));                                                        \
+            const unsigned off_ = (unsigned)min(ra_, hm2 - ra_) * pitch32;                              \
+            if (do_own) {                                                                               \
                 if constexpr (NOUT == 8) cp_async_16(my_s + (SO_), gown + off_, own_bytes);             \
                 else cp_async_8(my_s + (SO_), gown + off_, own_bytes);                                  \
             }                                                                                           \
@@ -437,9 +437,20 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
         configured = true;
     }
     const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
-    int rows = 16;
-    const long long want = (long long)sm_count * kWarpsPerBlock * 4;
-    while (rows > 2 && (long long)tiles_x * ((dh + rows - 1) / rows) * batch < want) rows >>= 1;
+    // Strip height: every warp task costs about (2*rows + 3 input rows + prologue); tasks run in rounds of
+    // `resident` warps (3 CTAs of 8 warps per SM at 72-80 registers).  Pick the height that minimises
+    // rounds x task cost -- tall strips amortise the 3 halo rows, but a nearly empty last round is pure loss.
+    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
+    int rows = 2;
+    double best = 1e300;
+    for (int r = 2; r <= 48; ++r) {
+        const int strips = (dh + r - 1) / r;
+        const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
+        const long long tasks = (long long)tiles_x * strips * batch;
+        const long long rounds = (tasks + resident - 1) / resident;
+        const double cost = (double)rounds * (2.0 * rr + 3.0 + 6.0);
+        if (cost < best) { best = cost; rows = rr; }
+    }
     const int strips_y = (dh + rows - 1) / rows;
     const long long n_tasks = (long long)tiles_x * strips_y * batch;
     const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
