@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU call: parity tests, bench (both arms), ncu launch list of the bench command, full ncu captures of the two kernels.
+# Usage (under gpurun): bash scripts/gpu_round.sh <tag>
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+tail -3 $OUT/pytest_gpu.log
+python bench.py --impl reference --steps 200 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+tail -c 600 $OUT/bench.err
+python bench.py --workload kitti_ref_params --steps 200 > $OUT/bench_win31.json 2>> $OUT/bench.err
+# launch list of the same bench command (cold-cache, serialised: shares only)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 40 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+# full captures: batched pyramid kernel (level 0->1 of 310 KITTI images) and the single-pair LK kernel
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pyr_down -c 3 -o $OUT/prof_pyr -f \
+    python scripts/prof_target.py pyr > $OUT/prof_pyr.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_fast -s 1 -c 2 -o $OUT/prof_lk -f \
+    python scripts/prof_target.py lk > $OUT/prof_lk.log 2>&1
+ls -la $OUT

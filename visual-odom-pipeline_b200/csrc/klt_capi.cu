@@ -289,7 +289,14 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     const size_t pts_bytes = align_up((size_t)n * 8, 256);
     const size_t off_out = off_pts + pts_bytes;                 // nextPts | err | status, one D2H copy
     const size_t out_bytes = (size_t)n * 8 + (size_t)n * 4 + (size_t)n;
-    s = ensure_device_ws(ctx, off_out + align_up(out_bytes, 256));
+    // raw landing zone: each image arrives as ONE contiguous DMA in the caller's own row pitch and is re-pitched on
+    // the device (a pitched 2-D copy of e.g. 1241-byte rows reaches a fraction of PCIe bandwidth)
+    const size_t off_raw = off_out + align_up(out_bytes, 256);
+    const size_t raw_prev = (size_t)(h - 1) * (size_t)prev_pitch + (size_t)w;
+    const size_t raw_next = (size_t)(h - 1) * (size_t)next_pitch + (size_t)w;
+    const bool linear = raw_prev <= 2 * (size_t)w * h && raw_next <= 2 * (size_t)w * h;
+    const size_t raw_slot = linear ? align_up((raw_prev > raw_next ? raw_prev : raw_next) + 32, 256) : 0;
+    s = ensure_device_ws(ctx, off_raw + 2 * raw_slot);
     if (s != KLT_OK) return s;
     s = ensure_host_ws(ctx, align_up(out_bytes, 256));
     if (s != KLT_OK) return s;
@@ -301,8 +308,21 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
         return std::chrono::duration<double, std::micro>(b - a).count();
     };
     const auto t0 = now();
-    KLT_CUDA(cudaMemcpy2DAsync(d + off_img, ipitch, prev_img, (size_t)prev_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
-    KLT_CUDA(cudaMemcpy2DAsync(d + off_img + ibytes, ipitch, next_img, (size_t)next_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+    if (linear) {
+        KLT_CUDA(cudaMemcpyAsync(d + off_raw, prev_img, raw_prev, cudaMemcpyHostToDevice, st));
+        KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, next_img, raw_next, cudaMemcpyHostToDevice, st));
+        if (prev_pitch == next_pitch) {
+            s = repitch_launch(d + off_raw, prev_pitch, (long long)raw_slot, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 2, st);
+        } else {
+            s = repitch_launch(d + off_raw, prev_pitch, 0, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 1, st);
+            if (s == KLT_OK)
+                s = repitch_launch(d + off_raw + raw_slot, next_pitch, 0, d + off_img + ibytes, (long long)ipitch, (long long)ibytes, w, h, 1, st);
+        }
+        if (s != KLT_OK) return s;
+    } else {
+        KLT_CUDA(cudaMemcpy2DAsync(d + off_img, ipitch, prev_img, (size_t)prev_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+        KLT_CUDA(cudaMemcpy2DAsync(d + off_img + ibytes, ipitch, next_img, (size_t)next_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+    }
     float* d_next = reinterpret_cast<float*>(d + off_out);
     float* d_err = reinterpret_cast<float*>(d + off_out + (size_t)n * 8);
     uint8_t* d_status = d + off_out + (size_t)n * 12;

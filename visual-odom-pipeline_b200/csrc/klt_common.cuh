@@ -44,6 +44,11 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
                            uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
                            cudaStream_t stream);
 
+// Copies n_img tightly/oddly pitched u8 images (image i at src + i * sbatch, rows spitch apart, any alignment) into
+// 16-byte-aligned pitched storage.  The source buffer must be readable up to 16 bytes past the last pixel.
+klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
+                          long long dbatch, int w, int h, int n_img, cudaStream_t stream);
+
 struct LKLaunch {
     PyrView prev, next;
     const float* prev_pts;

@@ -836,11 +836,11 @@ klt_status launch_wpp(const LKLaunch& L, int wpp, cudaStream_t stream)
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream)
 {
     const long long total = (long long)L.n_per_pair * L.batch;
-    // warps per point: fill the chip once (about 32 resident warps per SM), then prefer fewer warps per point
-    int wpp = 1;
-    const long long resident = (long long)sm_count * 32;
-    if (total * 4 <= resident * 2) wpp = 4;
-    else if (total * 2 <= resident * 2) wpp = 2;
+    // warps per point, from measurements on B200 (profiles/): the kernel is latency-bound, so more warps per point win
+    // until the per-iteration overhead replicated in every warp dominates: 31x31 -> always 4; 21x21 -> 4 while the
+    // points fit the chip about once, else 2.  One warp per point never wins (register-limited occupancy).
+    int wpp = 4;
+    if (L.win_w * L.win_h <= 21 * 21 && total > (long long)sm_count * 32) wpp = 2;
     if (forced_wpp == 1 || forced_wpp == 2 || forced_wpp == 4) wpp = forced_wpp;
     if (L.win_w == 21 && L.win_h == 21) return launch_wpp<21, 21>(L, wpp, stream);
     if (L.win_w == 31 && L.win_h == 31) return launch_wpp<31, 31>(L, wpp, stream);

@@ -24,6 +24,7 @@
 #include "klt_common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace klt {
 
@@ -36,6 +37,12 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
+}
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 // (b0, 0, b2, 0) and (b1, 0, b3, 0) of a word: even / odd columns as packed u16x2
 __device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return prmt(w, 0u, 0x4240u); }
@@ -199,17 +206,17 @@ struct RingCfg {
     static constexpr int WARP_BYTES = kRing * SLOT;
 };
 
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes)
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int src_bytes)
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -241,40 +248,20 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a)
 }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// One warp task: output rows [y0, y1) of the tile whose first input column is X0 (NOUT outputs per lane).
 template <int NOUT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
-pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
-                     uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
-                     int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+__device__ __forceinline__ void ring_task(const uint8_t* __restrict__ simg, int w, int h, long long spitch,
+                                          uint8_t* __restrict__ dimg, int dw, long long dpitch, int X0, int y0, int y1,
+                                          uint32_t ring_s, int lane)
 {
     using RC = RingCfg<NOUT>;
     constexpr int NW = NOUT / 2;
-    constexpr int NP = NOUT + 3;
-    extern __shared__ __align__(128) uint8_t ring_smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
-
-    const int tx = (int)(task % tiles_x);
-    const long long t2 = task / tiles_x;
-    const int sy = (int)(t2 % strips_y);
-    const int b = (int)(t2 / strips_y);
-    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
-
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RC::WARP_BYTES);
-    const int X0 = tx * RC::BODY;                 // first input column of the tile
     const int cb = X0 + 2 * NOUT * lane;          // first own input column
-    const int own_bytes = max(0, min(2 * NOUT, w - cb));
-    const int y0 = sy * rows_per_strip;
-    const int y1 = min(y0 + rows_per_strip, dh);
     const int n_rows = 2 * (y1 - y0) + 3;         // input rows 2*y0-2 .. 2*y1
     const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
     const uint8_t* __restrict__ gown = simg + cb;
     // one extra 4-byte halo copy per row: lane 0 fetches columns X0-4..X0-1, lane 31 columns X0+BODY..X0+BODY+3
-    const int rb = max(0, min(4, w - (X0 + RC::BODY)));
-    const bool has_x = (lane == 0 && X0 > 0) || (lane == 31 && rb > 0);
-    const int x_bytes = (lane == 0) ? 4 : rb;
+    const bool has_x = (lane == 0 && X0 > 0) || (lane == 31 && X0 + RC::BODY < w);
     const uint32_t x_s = ring_s + ((lane == 0) ? 12u : (uint32_t)(16 + RC::BODY));
     const uint8_t* __restrict__ gx = simg + ((lane == 0) ? (X0 - 4) : (X0 + RC::BODY));
     const int hm2 = 2 * h - 2;
@@ -282,18 +269,20 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
 
     // input row i of the strip = image row 2*y0-2+i under REFLECT_101; for -h < r < 2h-1 that is
     // min(|r|, 2h-2-|r|), branch-free.  SO_ = compile-time ring slot offset.  One commit group per row, always.
+    // Copies are whole 16/8/4-byte granules: a granule that holds at least one pixel lies inside the 16-byte-pitched
+    // row, and the bytes past column w-1 it may bring along are never used (columns w, w+1 are patched below).
     const int r_first = 2 * y0 - 2;
-    const bool do_own = own_bytes > 0;
+    const bool do_own = cb < w;
 #define KLT_ISSUE(i_, SO_)                                                                              \
     do {                                                                                                \
         if ((i_) < n_rows) { /* warp-uniform */                                                         \
             const int ra_ = abs(r_first + (i_));                                                        \
-            const unsigned off_ = (unsigned)min(ra_, hm2 - ra_) * pitch32;                              \
+            const unsigned long long off_ = (unsigned long long)(unsigned)min(ra_, hm2 - ra_) * pitch32; \
             if (do_own) {                                                                               \
-                if constexpr (NOUT == 8) cp_async_16(my_s + (SO_), gown + off_, own_bytes);             \
-                else cp_async_8(my_s + (SO_), gown + off_, own_bytes);                                  \
+                if constexpr (NOUT == 8) cp_async_16(my_s + (SO_), gown + off_);                        \
+                else cp_async_8(my_s + (SO_), gown + off_);                                             \
             }                                                                                           \
-            if (has_x) cp_async_4(x_s + (SO_), gx + off_, x_bytes);                                     \
+            if (has_x) cp_async_4(x_s + (SO_), gx + off_);                                              \
         }                                                                                               \
         cp_async_commit();                                                                              \
     } while (0)
@@ -310,28 +299,29 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
     } while (0)
 
     const bool fix_left = (X0 == 0) && (lane == 0);
-#define KLT_LOAD_ROW(SO_, p_)                                                                           \
+    // Words of one landed row: W[0] = the 4 bytes left of the own bytes, W[1..NW] = own bytes, W[NW+1] = the 4 bytes right.
+#define KLT_LOAD_ROW(SO_, W_)                                                                           \
     do {                                                                                                \
         const uint32_t a_ = my_s + (SO_);                                                               \
-        uint32_t wv_[NW];                                                                               \
         if constexpr (NOUT == 8) {                                                                      \
             const uint4 v_ = lds_v4(a_);                                                                \
-            wv_[0] = v_.x; wv_[1] = v_.y; wv_[2] = v_.z; wv_[3] = v_.w;                                 \
+            (W_)[1] = v_.x; (W_)[2] = v_.y; (W_)[3] = v_.z; (W_)[4] = v_.w;                             \
         } else {                                                                                        \
             const uint2 v_ = lds_v2(a_);                                                                \
-            wv_[0] = v_.x; wv_[1] = v_.y;                                                               \
+            (W_)[1] = v_.x; (W_)[2] = v_.y;                                                             \
         }                                                                                               \
-        uint32_t l_ = lds_u32(a_ - 4);                                                                  \
-        const uint32_t r_ = lds_u32(a_ + 2 * NOUT);                                                     \
-        if (fix_left) l_ = prmt(wv_[0], wv_[0], 0x1200u); /* columns -2,-1 mirror 2,1 */                \
-        (p_)[0] = even_bytes(l_);                                                                       \
-        (p_)[1] = odd_bytes(l_);                                                                        \
-        _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                             \
-            (p_)[2 + 2 * k_] = even_bytes(wv_[k_]);                                                     \
-            (p_)[3 + 2 * k_] = odd_bytes(wv_[k_]);                                                      \
-        }                                                                                               \
-        (p_)[NOUT + 2] = even_bytes(r_);                                                                \
+        (W_)[0] = lds_u32(a_ - 4);                                                                      \
+        (W_)[NW + 1] = lds_u32(a_ + 2 * NOUT);                                                          \
+        if (fix_left) (W_)[0] = prmt((W_)[1], (W_)[1], 0x1200u); /* columns -2,-1 mirror 2,1 */         \
     } while (0)
+    // Horizontal 5-tap [1 4 6 4 1] * M_ on raw bytes with two dp4a per output: output 2k is centred on byte 0 of own
+    // word k (taps: bytes 2,3 of the word before, bytes 0..2 of the word), output 2k+1 on byte 2 (bytes 0..3 of the
+    // word, byte 0 of the next).  INIT_[j] seeds the accumulators, so vertical weights and sums ride along for free.
+#define KLT_HORIZ(W_, M_, INIT_, OUT_)                                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                                 \
+        (OUT_)[2 * k_] = dp4a_uu((W_)[k_], 0x04010000u * (M_), dp4a_uu((W_)[k_ + 1], 0x00010406u * (M_), (INIT_)[2 * k_]));          \
+        (OUT_)[2 * k_ + 1] = dp4a_uu((W_)[k_ + 1], 0x04060401u * (M_), dp4a_uu((W_)[k_ + 2], 0x00000001u * (M_), (INIT_)[2 * k_ + 1])); \
+    }
 #define KLT_SLOT(i_) ((uint32_t)((((i_) % kRing + kRing) % kRing) * RC::SLOT))
 
     KLT_ISSUE(0, KLT_SLOT(0)); KLT_ISSUE(1, KLT_SLOT(1)); KLT_ISSUE(2, KLT_SLOT(2)); KLT_ISSUE(3, KLT_SLOT(3));
@@ -342,103 +332,573 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
         KLT_FIX_RIGHT(KLT_SLOT(0)); KLT_FIX_RIGHT(KLT_SLOT(1)); KLT_FIX_RIGHT(KLT_SLOT(2));
         __syncwarp();
     }
-    uint32_t tprev[NP], rc[NP];
-    {
-        uint32_t pa[NP], pb[NP];
-        KLT_LOAD_ROW(KLT_SLOT(0), pa);
-        KLT_LOAD_ROW(KLT_SLOT(1), pb);
-        KLT_LOAD_ROW(KLT_SLOT(2), rc);
+    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r):
+    //   E_y = h_{2y} + 16,  P_y = E_y + 4 h_{2y+1},  V_y = P_{y-1} + P_y + 5 E_y + E_{y+1}
+    //       = h_{2y-2} + 4 h_{2y-1} + 6 h_{2y} + 4 h_{2y+1} + h_{2y+2} + 128;   dst = V_y >> 8   (V_y <= 65408)
+    // Every input row gets exactly one horizontal pass; the x4 of the odd rows is folded into the dp4a coefficients.
+    uint32_t e_cur[NOUT], p_prev[NOUT], k16[NOUT];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) tprev[i] = pa[i] + 4u * pb[i] + rc[i];
+    for (int i = 0; i < NOUT; ++i) k16[i] = 16u;
+    {
+        uint32_t wa[NW + 2], wb[NW + 2], wc[NW + 2], e_m1[NOUT];
+        KLT_LOAD_ROW(KLT_SLOT(0), wa);
+        KLT_LOAD_ROW(KLT_SLOT(1), wb);
+        KLT_LOAD_ROW(KLT_SLOT(2), wc);
+        KLT_HORIZ(wa, 1u, k16, e_m1);
+        KLT_HORIZ(wb, 4u, e_m1, p_prev);
+        KLT_HORIZ(wc, 1u, k16, e_cur);
     }
     const int xo = cb >> 1;
-    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
+    uint8_t* __restrict__ drow = dimg + (long long)y0 * dpitch + xo;
     const bool full_store = (xo + NOUT <= dw);
     const int n_out = y1 - y0;
 
     // one output row; K_ = t % 4 fixes every ring slot offset at compile time (rows 2t+3, 2t+4 are consumed, rows
     // 2t+7, 2t+8 are issued into the slots of rows 2t-1, 2t, last read two iterations ago)
-#define KLT_STEP(K_)                                                                                    \
+#define KLT_STEP(K_, FIX_)                                                                                \
     do {                                                                                                \
         cp_async_wait<2>(); /* rows <= 2t+4 have landed; the two newest groups may still be in flight */ \
         __syncwarp();                                                                                   \
-        if (fix_right) {                                                                                \
+        if (FIX_) {                                                                                     \
             KLT_FIX_RIGHT(KLT_SLOT(2 * (K_) + 3)); KLT_FIX_RIGHT(KLT_SLOT(2 * (K_) + 4));               \
             __syncwarp();                                                                               \
         }                                                                                               \
-        uint32_t ro[NP], re[NP];                                                                        \
-        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 3), ro);                                                       \
-        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 4), re);                                                       \
+        uint32_t wo[NW + 2], we[NW + 2];                                                                \
+        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 3), wo);                                                       \
+        KLT_LOAD_ROW(KLT_SLOT(2 * (K_) + 4), we);                                                       \
         KLT_ISSUE(2 * t + 7, KLT_SLOT(2 * (K_) + 7));                                                   \
         KLT_ISSUE(2 * t + 8, KLT_SLOT(2 * (K_) + 8));                                                   \
-        uint32_t v[NP];                                                                                 \
-        _Pragma("unroll") for (int i = 0; i < NP; ++i) {                                                \
-            const uint32_t tt = rc[i] + 4u * ro[i] + re[i];                                             \
-            v[i] = tprev[i] + tt + 4u * rc[i];                                                          \
-            tprev[i] = tt;                                                                              \
-            rc[i] = re[i];                                                                              \
-        }                                                                                               \
-        uint32_t s_[NW];                                                                                \
-        _Pragma("unroll") for (int i = 0; i < NW; ++i) {                                                \
-            const uint32_t e_m = v[2 * i], o_m = v[2 * i + 1];                                          \
-            const uint32_t e_c = v[2 * i + 2], o_c = v[2 * i + 3];                                      \
-            const uint32_t e_p = v[2 * i + 4];                                                          \
-            const uint32_t a = __funnelshift_r(e_m, e_c, 16);                                           \
-            const uint32_t c = __funnelshift_r(e_c, e_p, 16);                                           \
-            const uint32_t oa = __funnelshift_r(o_m, o_c, 16);                                          \
-            s_[i] = a + c + 6u * e_c + 4u * (oa + o_c) + 0x00800080u;                                   \
+        uint32_t p_cur[NOUT], e_nxt[NOUT], v_[NOUT];                                                    \
+        KLT_HORIZ(wo, 4u, e_cur, p_cur);                                                                \
+        KLT_HORIZ(we, 1u, k16, e_nxt);                                                                  \
+        _Pragma("unroll") for (int i = 0; i < NOUT; ++i) {                                              \
+            v_[i] = (5u * e_cur[i] + p_cur[i]) + (p_prev[i] + e_nxt[i]);                                \
+            p_prev[i] = p_cur[i];                                                                       \
+            e_cur[i] = e_nxt[i];                                                                        \
         }                                                                                               \
         if (full_store) {                                                                               \
+            /* byte 1 of every V: pair two V's into one word (V < 2^16), then one PRMT per 4 outputs */ \
             if constexpr (NOUT == 8) {                                                                  \
                 uint2 o;                                                                                \
-                o.x = prmt(s_[0], s_[1], 0x7531u);                                                      \
-                o.y = prmt(s_[2], s_[NW - 1], 0x7531u);                                                 \
+                o.x = prmt(v_[1] * 65536u + v_[0], v_[3] * 65536u + v_[2], 0x7531u);                    \
+                o.y = prmt(v_[5] * 65536u + v_[4], v_[7] * 65536u + v_[6], 0x7531u);                    \
                 *reinterpret_cast<uint2*>(drow) = o;                                                    \
             } else {                                                                                    \
-                *reinterpret_cast<uint32_t*>(drow) = prmt(s_[0], s_[1], 0x7531u);                       \
+                *reinterpret_cast<uint32_t*>(drow) = prmt(v_[1] * 65536u + v_[0], v_[3] * 65536u + v_[2], 0x7531u); \
             }                                                                                           \
         } else {                                                                                        \
-            _Pragma("unroll") for (int i = 0; i < NW; ++i) {                                            \
-                if (xo + 2 * i < dw) drow[2 * i] = (uint8_t)(s_[i] >> 8);                               \
-                if (xo + 2 * i + 1 < dw) drow[2 * i + 1] = (uint8_t)(s_[i] >> 24);                      \
-            }                                                                                           \
+            _Pragma("unroll") for (int i = 0; i < NOUT; ++i)                                            \
+                if (xo + i < dw) drow[i] = (uint8_t)(v_[i] >> 8);                                       \
         }                                                                                               \
         drow += dpitch;                                                                                 \
         ++t;                                                                                            \
     } while (0)
 
-    for (int t = 0; t < n_out;) {
-        KLT_STEP(0);
-        if (t >= n_out) break;
-        KLT_STEP(1);
-        if (t >= n_out) break;
-        KLT_STEP(2);
-        if (t >= n_out) break;
-        KLT_STEP(3);
+#define KLT_LOOP(FIX_)                                                                                  \
+    for (int t = 0; t < n_out;) {                                                                       \
+        KLT_STEP(0, FIX_);                                                                              \
+        if (t >= n_out) break;                                                                          \
+        KLT_STEP(1, FIX_);                                                                              \
+        if (t >= n_out) break;                                                                          \
+        KLT_STEP(2, FIX_);                                                                              \
+        if (t >= n_out) break;                                                                          \
+        KLT_STEP(3, FIX_);                                                                              \
     }
+    // the right-edge patch is needed by the last tile of a row only: keep it (and its warp barrier) out of the others
+    if (fix_right) { KLT_LOOP(true) } else { KLT_LOOP(false) }
+#undef KLT_LOOP
     cp_async_wait<0>();
 #undef KLT_STEP
 #undef KLT_SLOT
 #undef KLT_ISSUE
 #undef KLT_FIX_RIGHT
 #undef KLT_LOAD_ROW
+#undef KLT_HORIZ
+}
+
+// Tiles of one image row: n8 full 512-column tiles (8 outputs per lane), then at most one remainder tile that uses
+// 4 outputs per lane when the remainder fits 256 columns (KITTI: 1241 = 2 x 512 + 217 -> 97 % of the lanes busy
+// instead of 81 % with three 512-column tiles).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
+                     uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                     int rows_per_strip, int tiles_x, int n8, int rem_nout, int strips_y, long long n_tasks)
+{
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+    const int tx = (int)(task % tiles_x);
+    const long long t2 = task / tiles_x;
+    const int sy = (int)(t2 % strips_y);
+    const int b = (int)(t2 / strips_y);
+    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
+    uint8_t* __restrict__ dimg = dst + (long long)b * dbatch;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RingCfg<8>::WARP_BYTES);
+    const int X0 = tx * RingCfg<8>::BODY;
+    const int y0 = sy * rows_per_strip;
+    const int y1 = min(y0 + rows_per_strip, dh);
+    if (tx < n8 || rem_nout == 8) ring_task<8>(simg, w, h, spitch, dimg, dw, dpitch, X0, y0, y1, ring_s, lane);
+    else ring_task<4>(simg, w, h, spitch, dimg, dw, dpitch, X0, y0, y1, ring_s, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Main kernel, bulk-copy variant: the per-warp row ring is filled by the TMA engine.  One lane issues ONE
+// cp.async.bulk (UBLKCP) per input row that lands the warp's whole 16-byte-aligned row segment -- own bytes and both
+// halos -- in a ring slot and signals the slot's mbarrier; the other lanes spend no instructions on address math or
+// copies, and the ring can be deep (14 rows = 7.4 KB in flight per warp, ~180 KB per SM) at no register cost.
+constexpr int kBulkRing = 16;
+
+template <int NOUT>
+struct BulkCfg {
+    static constexpr int BODY = 64 * NOUT;
+    static constexpr int SLOT = BODY + 32;              // [16 left halo][BODY][16 right halo], 16-byte granules
+    static constexpr int WARP_BYTES = kBulkRing * SLOT + kBulkRing * 8;   // slots + one mbarrier each
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KLT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KLT_DONE_%=;\n"
+        "bra KLT_WAIT_%=;\n"
+        "KLT_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 template <int NOUT>
-klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
-                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
+                     uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                     int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
 {
-    using RC = RingCfg<NOUT>;
+    using BC = BulkCfg<NOUT>;
+    constexpr int NW = NOUT / 2;
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+
+    const int tx = (int)(task % tiles_x);
+    const long long t2 = task / tiles_x;
+    const int sy = (int)(t2 % strips_y);
+    const int b = (int)(t2 / strips_y);
+    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
+
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * BC::WARP_BYTES);
+    const uint32_t bars_s = ring_s + kBulkRing * BC::SLOT;
+    const int X0 = tx * BC::BODY;                 // first input column of the tile
+    const int cb = X0 + 2 * NOUT * lane;          // first own input column
+    const int y0 = sy * rows_per_strip;
+    const int y1 = min(y0 + rows_per_strip, dh);
+    const int n_out = y1 - y0;
+    const int n_rows = 2 * n_out + 3;             // input rows 2*y0-2 .. 2*y1
+    const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
+    // the row segment one copy moves: whole 16-byte granules that hold at least one pixel of columns [X0-16, X0+BODY+16)
+    const int g0 = max(X0 - 16, 0);
+    const int g1 = min(X0 + BC::BODY + 16, (w + 15) & ~15);
+    const uint32_t seg_bytes = (uint32_t)(g1 - g0);
+    const uint32_t seg_s = ring_s + (uint32_t)(g0 - (X0 - 16));
+    const uint8_t* __restrict__ gseg = simg + g0;
+    const int hm2 = 2 * h - 2;
+    const unsigned pitch32 = (unsigned)spitch;    // h * pitch < 2^31 is checked by the launcher
+    const int r_first = 2 * y0 - 2;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kBulkRing; ++i) mbar_init(bars_s + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (min(|r|, 2h-2-|r|) for -h < r < 2h-1); it lives in
+    // slot i % kBulkRing and completes phase (i / kBulkRing) & 1 of that slot's mbarrier.
+    auto issue = [&](int i) {
+        if (i < n_rows) {
+            const int ra = abs(r_first + i);
+            const unsigned long long off = (unsigned long long)(unsigned)min(ra, hm2 - ra) * pitch32;
+            const uint32_t so = (uint32_t)(i & (kBulkRing - 1));
+            mbar_expect_tx(bars_s + 8 * so, seg_bytes);
+            bulk_g2s(seg_s + so * BC::SLOT, gseg + off, seg_bytes, bars_s + 8 * so);
+        }
+    };
+    auto wait_row = [&](int i) { mbar_wait(bars_s + 8 * (uint32_t)(i & (kBulkRing - 1)), (uint32_t)(i / kBulkRing) & 1u); };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int i = 0; i < kBulkRing; ++i) issue(i);
+    }
+
+    // REFLECT_101 at the right image edge: columns w, w+1 mirror w-2, w-3; patched inside the landed slot by two
+    // lanes (the sources are always inside the slot: body or left halo).  The left edge is fixed in registers.
+    const bool fix_right = (w < X0 + BC::BODY + 4);
+    const int fr_c = w - X0 + lane;                  // lane 0: column w (mirror: -2), lane 1: column w+1 (mirror: -4)
+    const bool fr_on = (lane < 2) && (fr_c < BC::BODY + 4);
+    const uint32_t fr_dst = ring_s + 16 + fr_c, fr_src = fr_dst - 2 - 2 * lane;
+    const bool fix_left = (X0 == 0) && (lane == 0);
+    auto patch_right = [&](int i) {
+        const uint32_t so = (uint32_t)(i & (kBulkRing - 1)) * BC::SLOT;
+        if (fr_on) sts_u8(fr_dst + so, lds_u8(fr_src + so));
+    };
+    // Words of one landed row: W[0] = the 4 bytes left of the own bytes, W[1..NW] = own bytes, W[NW+1] = the 4 bytes right.
+    auto load_row = [&](int i, uint32_t (&W)[NW + 2]) {
+        const uint32_t a = my_s + (uint32_t)(i & (kBulkRing - 1)) * BC::SLOT;
+        if constexpr (NOUT == 8) {
+            const uint4 v = lds_v4(a);
+            W[1] = v.x; W[2] = v.y; W[3] = v.z; W[4] = v.w;
+        } else {
+            const uint2 v = lds_v2(a);
+            W[1] = v.x; W[2] = v.y;
+        }
+        W[0] = lds_u32(a - 4);
+        W[NW + 1] = lds_u32(a + 2 * NOUT);
+        if (fix_left) W[0] = prmt(W[1], W[1], 0x1200u);   // columns -2,-1 mirror 2,1
+    };
+#define KLT_HORIZ(W_, M_, INIT_, OUT_)                                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                                 \
+        (OUT_)[2 * k_] = dp4a_uu((W_)[k_], 0x04010000u * (M_), dp4a_uu((W_)[k_ + 1], 0x00010406u * (M_), (INIT_)[2 * k_]));          \
+        (OUT_)[2 * k_ + 1] = dp4a_uu((W_)[k_ + 1], 0x04060401u * (M_), dp4a_uu((W_)[k_ + 2], 0x00000001u * (M_), (INIT_)[2 * k_ + 1])); \
+    }
+
+    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r), see pyr_down_ring_kernel:
+    //   E_y = h_{2y} + 16,  P_y = E_y + 4 h_{2y+1},  V_y = P_{y-1} + P_y + 5 E_y + E_{y+1},  dst = V_y >> 8
+    uint32_t e_cur[NOUT], p_prev[NOUT], k16[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) k16[i] = 16u;
+    wait_row(0); wait_row(1); wait_row(2);
+    if (fix_right) {      // warp-uniform
+        patch_right(0); patch_right(1); patch_right(2);
+        __syncwarp();
+    }
+    {
+        uint32_t wa[NW + 2], wb[NW + 2], wc[NW + 2], e_m1[NOUT];
+        load_row(0, wa);
+        load_row(1, wb);
+        load_row(2, wc);
+        KLT_HORIZ(wa, 1u, k16, e_m1);
+        KLT_HORIZ(wb, 4u, e_m1, p_prev);
+        KLT_HORIZ(wc, 1u, k16, e_cur);
+    }
+    __syncwarp();   // every lane has read rows 0..2: slot 0 may be refilled
+    if (lane == 0) {
+        if (fix_right) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(kBulkRing);
+    }
+    const int xo = cb >> 1;
+    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
+    const bool full_store = (xo + NOUT <= dw);
+
+#pragma unroll 2
+    for (int t = 0; t < n_out; ++t) {
+        // rows <= 2t+2 were read by every lane in earlier iterations: their slots take rows 2t+1+R, 2t+2+R
+        __syncwarp();
+        if (lane == 0) {
+            if (fix_right) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(2 * t + 1 + kBulkRing);
+            issue(2 * t + 2 + kBulkRing);
+        }
+        wait_row(2 * t + 3);
+        wait_row(2 * t + 4);
+        if (fix_right) {
+            patch_right(2 * t + 3); patch_right(2 * t + 4);
+            __syncwarp();
+        }
+        uint32_t wo[NW + 2], we[NW + 2];
+        load_row(2 * t + 3, wo);
+        load_row(2 * t + 4, we);
+        uint32_t p_cur[NOUT], e_nxt[NOUT], v[NOUT];
+        KLT_HORIZ(wo, 4u, e_cur, p_cur);
+        KLT_HORIZ(we, 1u, k16, e_nxt);
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) {
+            v[i] = (5u * e_cur[i] + p_cur[i]) + (p_prev[i] + e_nxt[i]);
+            p_prev[i] = p_cur[i];
+            e_cur[i] = e_nxt[i];
+        }
+        if (full_store) {
+            // byte 1 of every V: pair two V's into one word (V < 2^16), then one PRMT per 4 outputs
+            if constexpr (NOUT == 8) {
+                uint2 o;
+                o.x = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
+                o.y = prmt(v[5] * 65536u + v[4], v[7] * 65536u + v[6], 0x7531u);
+                *reinterpret_cast<uint2*>(drow) = o;
+            } else {
+                *reinterpret_cast<uint32_t*>(drow) = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i)
+                if (xo + i < dw) drow[i] = (uint8_t)(v[i] >> 8);
+        }
+        drow += dpitch;
+    }
+#undef KLT_HORIZ
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cp.async ring with run-time slot indexing and a template ring depth (RING rows per warp, RING - 4 of them in flight).
+template <int NOUT, int RING, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+pyr_down_ring2_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
+                      uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                      int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+{
+    constexpr int BODY = 64 * NOUT, SLOT = BODY + 32, NW = NOUT / 2;
+    static_assert((RING & (RING - 1)) == 0 && RING >= 8, "ring depth must be a power of two");
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+
+    const int tx = (int)(task % tiles_x);
+    const long long t2 = task / tiles_x;
+    const int sy = (int)(t2 % strips_y);
+    const int b = (int)(t2 / strips_y);
+    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
+
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RING * SLOT);
+    const int X0 = tx * BODY;                     // first input column of the tile
+    const int cb = X0 + 2 * NOUT * lane;          // first own input column
+    const int y0 = sy * rows_per_strip;
+    const int y1 = min(y0 + rows_per_strip, dh);
+    const int n_out = y1 - y0;
+    const int n_rows = 2 * n_out + 3;             // input rows 2*y0-2 .. 2*y1
+    const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
+    const uint8_t* __restrict__ gown = simg + cb;
+    // one extra 4-byte halo copy per row: lane 0 fetches columns X0-4..X0-1, lane 31 columns X0+BODY..X0+BODY+3
+    const bool has_x = (lane == 0 && X0 > 0) || (lane == 31 && X0 + BODY < w);
+    const uint32_t x_s = ring_s + ((lane == 0) ? 12u : (uint32_t)(16 + BODY));
+    const uint8_t* __restrict__ gx = simg + ((lane == 0) ? (X0 - 4) : (X0 + BODY));
+    const int hm2 = 2 * h - 2;
+    const unsigned pitch32 = (unsigned)spitch;    // h * pitch < 2^31 is checked by the launcher
+    const int r_first = 2 * y0 - 2;
+    const bool do_own = cb < w;
+
+    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (min(|r|, 2h-2-|r|) for -h < r < 2h-1), slot i % RING.
+    // Copies are whole 16/8/4-byte granules: a granule that holds at least one pixel lies inside the 16-byte-pitched row,
+    // and the bytes past column w-1 it may bring along are never used.  One commit group per row, always.
+    auto issue = [&](int i) {
+        if (i < n_rows) {   // warp-uniform
+            const int ra = abs(r_first + i);
+            const unsigned long long off = (unsigned long long)(unsigned)min(ra, hm2 - ra) * pitch32;
+            const uint32_t so = (uint32_t)(i & (RING - 1)) * SLOT;
+            if (do_own) {
+                if constexpr (NOUT == 8) cp_async_16(my_s + so, gown + off);
+                else cp_async_8(my_s + so, gown + off);
+            }
+            if (has_x) cp_async_4(x_s + so, gx + off);
+        }
+        cp_async_commit();
+    };
+    const bool fix_right = (w < X0 + BODY + 4);
+    const int fr_c = w - X0 + lane;                  // lane 0: column w (mirror: -2), lane 1: column w+1 (mirror: -4)
+    const bool fr_on = (lane < 2) && (fr_c < BODY + 4);
+    const uint32_t fr_dst = ring_s + 16 + fr_c, fr_src = fr_dst - 2 - 2 * lane;
+    const bool fix_left = (X0 == 0) && (lane == 0);
+    auto patch_right = [&](int i) {
+        const uint32_t so = (uint32_t)(i & (RING - 1)) * SLOT;
+        if (fr_on) sts_u8(fr_dst + so, lds_u8(fr_src + so));
+    };
+    auto load_row = [&](int i, uint32_t (&W)[NW + 2]) {
+        const uint32_t a = my_s + (uint32_t)(i & (RING - 1)) * SLOT;
+        if constexpr (NOUT == 8) {
+            const uint4 v = lds_v4(a);
+            W[1] = v.x; W[2] = v.y; W[3] = v.z; W[4] = v.w;
+        } else {
+            const uint2 v = lds_v2(a);
+            W[1] = v.x; W[2] = v.y;
+        }
+        W[0] = lds_u32(a - 4);
+        W[NW + 1] = lds_u32(a + 2 * NOUT);
+        if (fix_left) W[0] = prmt(W[1], W[1], 0x1200u);   // columns -2,-1 mirror 2,1
+    };
+#define KLT_HORIZ(W_, M_, INIT_, OUT_)                                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                                 \
+        (OUT_)[2 * k_] = dp4a_uu((W_)[k_], 0x04010000u * (M_), dp4a_uu((W_)[k_ + 1], 0x00010406u * (M_), (INIT_)[2 * k_]));          \
+        (OUT_)[2 * k_ + 1] = dp4a_uu((W_)[k_ + 1], 0x04060401u * (M_), dp4a_uu((W_)[k_ + 2], 0x00000001u * (M_), (INIT_)[2 * k_ + 1])); \
+    }
+
+#pragma unroll
+    for (int i = 0; i < RING - 1; ++i) issue(i);
+    cp_async_wait<RING - 4>();   // rows 0, 1, 2 have landed
+    __syncwarp();
+    if (fix_right) {             // warp-uniform
+        patch_right(0); patch_right(1); patch_right(2);
+        __syncwarp();
+    }
+    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r):
+    //   E_y = h_{2y} + 16,  P_y = E_y + 4 h_{2y+1},  V_y = P_{y-1} + P_y + 5 E_y + E_{y+1}
+    //       = h_{2y-2} + 4 h_{2y-1} + 6 h_{2y} + 4 h_{2y+1} + h_{2y+2} + 128;   dst = V_y >> 8   (V_y <= 65408)
+    // Every input row gets exactly one horizontal pass; the x4 of the odd rows is folded into the dp4a coefficients.
+    uint32_t e_cur[NOUT], p_prev[NOUT], k16[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) k16[i] = 16u;
+    {
+        uint32_t wa[NW + 2], wb[NW + 2], wc[NW + 2], e_m1[NOUT];
+        load_row(0, wa);
+        load_row(1, wb);
+        load_row(2, wc);
+        KLT_HORIZ(wa, 1u, k16, e_m1);
+        KLT_HORIZ(wb, 4u, e_m1, p_prev);
+        KLT_HORIZ(wc, 1u, k16, e_cur);
+    }
+    const int xo = cb >> 1;
+    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
+    const bool full_store = (xo + NOUT <= dw);
+
+    auto body = [&](auto fix_tag) {
+        constexpr bool FIX = decltype(fix_tag)::value;
+#pragma unroll 2
+        for (int t = 0; t < n_out; ++t) {
+            cp_async_wait<RING - 6>();   // rows <= 2t+4 have landed; the newest RING-6 groups may still be in flight
+            __syncwarp();
+            if (FIX) {
+                patch_right(2 * t + 3); patch_right(2 * t + 4);
+                __syncwarp();
+            }
+            uint32_t wo[NW + 2], we[NW + 2];
+            load_row(2 * t + 3, wo);
+            load_row(2 * t + 4, we);
+            // rows 2t-1, 2t were last read one iteration ago (all lanes passed the barrier above): refill their slots
+            issue(2 * t + RING - 1);
+            issue(2 * t + RING);
+            uint32_t p_cur[NOUT], e_nxt[NOUT], v[NOUT];
+            KLT_HORIZ(wo, 4u, e_cur, p_cur);
+            KLT_HORIZ(we, 1u, k16, e_nxt);
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) {
+                v[i] = (5u * e_cur[i] + p_cur[i]) + (p_prev[i] + e_nxt[i]);
+                p_prev[i] = p_cur[i];
+                e_cur[i] = e_nxt[i];
+            }
+            if (full_store) {
+                // byte 1 of every V: pair two V's into one word (V < 2^16), then one PRMT per 4 outputs
+                if constexpr (NOUT == 8) {
+                    uint2 o;
+                    o.x = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
+                    o.y = prmt(v[5] * 65536u + v[4], v[7] * 65536u + v[6], 0x7531u);
+                    *reinterpret_cast<uint2*>(drow) = o;
+                } else {
+                    *reinterpret_cast<uint32_t*>(drow) = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i)
+                    if (xo + i < dw) drow[i] = (uint8_t)(v[i] >> 8);
+            }
+            drow += dpitch;
+        }
+    };
+    // the right-edge patch is needed by the last tile of a row only: keep it (and its warp barrier) out of the others
+    if (fix_right) body(std::true_type{}); else body(std::false_type{});
+    cp_async_wait<0>();
+#undef KLT_HORIZ
+}
+
+template <int NOUT, int RING, int MINB>
+klt_status launch_ring2(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                        int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+{
     static bool configured = false;
-    const int smem = RC::WARP_BYTES * kWarpsPerBlock;
+    const int smem = RING * (64 * NOUT + 32) * kWarpsPerBlock;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring2_kernel<NOUT, RING, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
         configured = true;
     }
     const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
-    // Strip height: every warp task costs about (2*rows + 3 input rows + prologue); tasks run in rounds of
-    // `resident` warps (3 CTAs of 8 warps per SM at 72-80 registers).  Pick the height that minimises
+    const long long resident = (long long)sm_count * MINB * kWarpsPerBlock;
+    int rows = 2;
+    double best = 1e300;
+    for (int r = 2; r <= 64; ++r) {
+        const int strips = (dh + r - 1) / r;
+        const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
+        const long long tasks = (long long)tiles_x * strips * batch;
+        const long long rounds = (tasks + resident - 1) / resident;
+        const double cost = (double)rounds * (2.0 * rr + 3.0 + 6.0);
+        if (cost < best) { best = cost; rows = rr; }
+    }
+    const int strips_y = (dh + rows - 1) / rows;
+    const long long n_tasks = (long long)tiles_x * strips_y * batch;
+    const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    pyr_down_ring2_kernel<NOUT, RING, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+template <int NOUT>
+klt_status launch_bulk(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+{
+    using BC = BulkCfg<NOUT>;
+    static bool configured = false;
+    const int smem = BC::WARP_BYTES * kWarpsPerBlock;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_bulk_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (klt_status)e;
+        configured = true;
+    }
+    const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
+    // Strip height: a warp task costs about (2*rows + 3 input rows + pipeline fill); tasks run in rounds of `resident`
+    // warps (3 CTAs of 8 warps per SM).  Pick the height that minimises rounds x task cost -- tall strips amortise the
+    // 3 halo rows and the fill, but a nearly empty last round is pure loss.
+    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
+    int rows = 2;
+    double best = 1e300;
+    for (int r = 2; r <= 64; ++r) {
+        const int strips = (dh + r - 1) / r;
+        const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
+        const long long tasks = (long long)tiles_x * strips * batch;
+        const long long rounds = (tasks + resident - 1) / resident;
+        const double cost = (double)rounds * (2.0 * rr + 3.0 + 10.0);
+        if (cost < best) { best = cost; rows = rr; }
+    }
+    const int strips_y = (dh + rows - 1) / rows;
+    const long long n_tasks = (long long)tiles_x * strips_y * batch;
+    const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    pyr_down_bulk_kernel<NOUT><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+{
+    using RC = RingCfg<8>;
+    static bool configured = false;
+    const int smem = RC::WARP_BYTES * kWarpsPerBlock;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (klt_status)e;
+        configured = true;
+    }
+    const int n8 = w / RC::BODY, rem = w - n8 * RC::BODY;
+    const int rem_nout = (rem == 0) ? 0 : (rem <= RingCfg<4>::BODY ? 4 : 8);
+    const int tiles_x = n8 + (rem > 0);
+    // Strip height: every warp task costs about (2*rows + 3 input rows + pipeline fill); tasks run in rounds of
+    // `resident` warps (3 CTAs of 8 warps per SM at 80 registers).  Pick the height that minimises
     // rounds x task cost -- tall strips amortise the 3 halo rows, but a nearly empty last round is pure loss.
     const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
     int rows = 2;
@@ -455,8 +915,8 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
     const long long n_tasks = (long long)tiles_x * strips_y * batch;
     const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_down_ring_kernel<NOUT><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
-        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    pyr_down_ring_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, n8, rem_nout, strips_y, n_tasks);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
@@ -481,7 +941,45 @@ klt_status launch_t(const uint8_t* src, int w, int h, long long spitch, long lon
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
+// Row repitch: every thread produces 16 destination bytes from 5 aligned source words (funnel shift by the
+// source row's byte misalignment).  Used by the host entry points so the H2D transfer can be ONE contiguous DMA per
+// image (a pitched 2-D copy of 1241-byte rows runs at a fraction of PCIe speed).
+__global__ void __launch_bounds__(256)
+repitch_kernel(const uint8_t* __restrict__ src, long long spitch, long long sbatch, uint8_t* __restrict__ dst,
+               long long dpitch, long long dbatch, int w, int chunks, int h)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (t >= chunks * h) return;
+    const int y = t / chunks, c = t - y * chunks;
+    const uint8_t* s = src + (long long)i * sbatch + (long long)y * spitch + 16 * c;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh);
+    o.y = __funnelshift_r(w1, w2, sh);
+    o.z = __funnelshift_r(w2, w3, sh);
+    o.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4*>(dst + (long long)i * dbatch + (long long)y * dpitch + 16 * c) = o;
+    (void)w;
+}
+
 }  // namespace
+
+klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
+                          long long dbatch, int w, int h, int n_img, cudaStream_t stream)
+{
+    if (!src || !dst || w <= 0 || h <= 0 || n_img <= 0 || n_img > 65535) return KLT_ERR_INVALID_ARG;
+    if ((((uintptr_t)dst | (uintptr_t)dpitch | (uintptr_t)dbatch) & 15) != 0 || dpitch < (w + 15) / 16 * 16) return KLT_ERR_INVALID_ARG;
+    const int chunks = (w + 15) / 16;
+    if ((long long)chunks * h > 0x7fffff00LL) return KLT_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)(((long long)chunks * h + 255) / 256), n_img, 1);
+    repitch_kernel<<<grid, 256, 0, stream>>>(src, spitch, sbatch, dst, dpitch, dbatch, w, chunks, h);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
 
 klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, long long sbatch,
                            uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
@@ -497,8 +995,17 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
     const bool use8 = (t8 * 3 <= dw * 4) || (t8 == t4);
     static const char* force_fallback = getenv("KLT_PYR_FALLBACK");   // tests: exercise the shuffle/gather kernel
     if (aligned && w >= 4 && h >= 3 && (long long)h * spitch < 0x7fffffffLL && !(force_fallback && force_fallback[0] == '1')) {
-        return use8 ? launch_ring<8>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
-                    : launch_ring<4>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        static const char* force_ring = getenv("KLT_PYR_RING");   // A/B between the load paths
+        const char fr = force_ring ? force_ring[0] : '1';
+        if (fr == '2')
+            return use8 ? launch_ring2<8, 16, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
+                        : launch_ring2<4, 16, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        if (fr == '3')
+            return use8 ? launch_ring2<8, 8, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
+                        : launch_ring2<4, 8, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        if (fr == '1') return launch_ring(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        return use8 ? launch_bulk<8>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
+                    : launch_bulk<4>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
     }
     if (aligned) {
         return use8 ? launch_t<8, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
