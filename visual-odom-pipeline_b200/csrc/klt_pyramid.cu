@@ -23,6 +23,7 @@
 //    only; interior lanes never branch on coordinates.
 #include "klt_common.cuh"
 
+#include <cuda.h>
 #include <cstdlib>
 #include <type_traits>
 
@@ -419,7 +420,8 @@ __device__ __forceinline__ void ring_task(const uint8_t* __restrict__ simg, int 
 // Tiles of one image row: n8 full 512-column tiles (8 outputs per lane), then at most one remainder tile that uses
 // 4 outputs per lane when the remainder fits 256 columns (KITTI: 1241 = 2 x 512 + 217 -> 97 % of the lanes busy
 // instead of 81 % with three 512-column tiles).
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+template <int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
                      uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
                      int rows_per_strip, int tiles_x, int n8, int rem_nout, int strips_y, long long n_tasks)
@@ -444,18 +446,17 @@ pyr_down_ring_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Main kernel, bulk-copy variant: the per-warp row ring is filled by the TMA engine.  One lane issues ONE
-// cp.async.bulk (UBLKCP) per input row that lands the warp's whole 16-byte-aligned row segment -- own bytes and both
-// halos -- in a ring slot and signals the slot's mbarrier; the other lanes spend no instructions on address math or
-// copies, and the ring can be deep (14 rows = 7.4 KB in flight per warp, ~180 KB per SM) at no register cost.
-constexpr int kBulkRing = 16;
-
-template <int NOUT>
-struct BulkCfg {
-    static constexpr int BODY = 64 * NOUT;
-    static constexpr int SLOT = BODY + 32;              // [16 left halo][BODY][16 right halo], 16-byte granules
-    static constexpr int WARP_BYTES = kBulkRing * SLOT + kBulkRing * 8;   // slots + one mbarrier each
-};
+// Main kernel, TMA variant: the per-warp row ring is filled by the TMA engine.  One lane issues ONE
+// cp.async.bulk.tensor (UTMALDG) per stage of kRowsPerStage input rows; the box is the warp's whole row segment
+// (own bytes + both 16-byte halo granules) x kRowsPerStage rows and lands in the ring, signalling the stage's mbarrier.
+// The other lanes spend no instructions on addresses or copies.  Stages that touch the top / bottom image border
+// (REFLECT_101 rows) are filled row by row with 1-D bulk copies (UBLKCP) instead.
+constexpr int kRowsPerStage = 4;
+constexpr int kStages = 4;
+constexpr int kTmaRing = kRowsPerStage * kStages;   // ring slots (input rows) per warp
+constexpr int kTmaSlot = 64 * 8 + 32;               // [16 left halo][512 body][16 right halo]
+constexpr int kTmaWarpBytes = kTmaRing * kTmaSlot + 128;  // slots + kStages mbarriers (padded: keeps warps 128-B aligned)
+static_assert(kTmaWarpBytes % 128 == 0, "TMA destinations must be 128-byte aligned");
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -482,39 +483,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_g2s_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
 
 template <int NOUT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
-pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
-                     uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
-                     int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+__device__ __forceinline__ void tma_task(const CUtensorMap* __restrict__ map, const uint8_t* __restrict__ simg, int b, int w, int h,
+                                         long long spitch, uint8_t* __restrict__ dimg, int dw, long long dpitch, int X0, int y0,
+                                         int y1, uint32_t ring_s, int lane)
 {
-    using BC = BulkCfg<NOUT>;
-    constexpr int NW = NOUT / 2;
-    extern __shared__ __align__(128) uint8_t ring_smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
-
-    const int tx = (int)(task % tiles_x);
-    const long long t2 = task / tiles_x;
-    const int sy = (int)(t2 % strips_y);
-    const int b = (int)(t2 / strips_y);
-    const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
-
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * BC::WARP_BYTES);
-    const uint32_t bars_s = ring_s + kBulkRing * BC::SLOT;
-    const int X0 = tx * BC::BODY;                 // first input column of the tile
+    constexpr int NW = NOUT / 2, BODY = 64 * NOUT, SLOT = kTmaSlot;
+    const uint32_t bars_s = ring_s + kTmaRing * SLOT;
     const int cb = X0 + 2 * NOUT * lane;          // first own input column
-    const int y0 = sy * rows_per_strip;
-    const int y1 = min(y0 + rows_per_strip, dh);
     const int n_out = y1 - y0;
     const int n_rows = 2 * n_out + 3;             // input rows 2*y0-2 .. 2*y1
     const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
-    // the row segment one copy moves: whole 16-byte granules that hold at least one pixel of columns [X0-16, X0+BODY+16)
+    // border stages: the row segment one 1-D copy moves = whole 16-byte granules holding pixels of [X0-16, X0+BODY+16)
     const int g0 = max(X0 - 16, 0);
-    const int g1 = min(X0 + BC::BODY + 16, (w + 15) & ~15);
+    const int g1 = min(X0 + BODY + 16, (w + 15) & ~15);
     const uint32_t seg_bytes = (uint32_t)(g1 - g0);
     const uint32_t seg_s = ring_s + (uint32_t)(g0 - (X0 - 16));
     const uint8_t* __restrict__ gseg = simg + g0;
@@ -524,42 +512,53 @@ pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
 
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < kBulkRing; ++i) mbar_init(bars_s + 8 * i, 1);
+        for (int i = 0; i < kStages; ++i) mbar_init(bars_s + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (min(|r|, 2h-2-|r|) for -h < r < 2h-1); it lives in
-    // slot i % kBulkRing and completes phase (i / kBulkRing) & 1 of that slot's mbarrier.
-    auto issue = [&](int i) {
-        if (i < n_rows) {
-            const int ra = abs(r_first + i);
-            const unsigned long long off = (unsigned long long)(unsigned)min(ra, hm2 - ra) * pitch32;
-            const uint32_t so = (uint32_t)(i & (kBulkRing - 1));
-            mbar_expect_tx(bars_s + 8 * so, seg_bytes);
-            bulk_g2s(seg_s + so * BC::SLOT, gseg + off, seg_bytes, bars_s + 8 * so);
+    // stage k = strip rows [4k, 4k+4) = image rows r_first + 4k ... ; it lives in ring slots (4k .. 4k+3) % kTmaRing and
+    // completes phase (k / kStages) & 1 of mbarrier k % kStages.
+    auto issue_stage = [&](int k) {
+        const int i0 = kRowsPerStage * k;
+        if (i0 < n_rows) {
+            const int R0 = r_first + i0;
+            const uint32_t bar = bars_s + 8 * (uint32_t)(k & (kStages - 1));
+            const uint32_t so = (uint32_t)(i0 & (kTmaRing - 1)) * SLOT;
+            if (R0 >= 0 && R0 + kRowsPerStage <= h) {
+                mbar_expect_tx(bar, kRowsPerStage * SLOT);
+                tma_g2s_3d(ring_s + so, map, (X0 - 16) >> 2, R0, b, bar);
+            } else {
+                const int nv = min(kRowsPerStage, n_rows - i0);
+                mbar_expect_tx(bar, (uint32_t)nv * seg_bytes);
+                for (int j = 0; j < nv; ++j) {
+                    const int ra = abs(R0 + j);
+                    const unsigned long long off = (unsigned long long)(unsigned)min(ra, hm2 - ra) * pitch32;
+                    bulk_g2s(seg_s + so + (uint32_t)j * SLOT, gseg + off, seg_bytes, bar);
+                }
+            }
         }
     };
-    auto wait_row = [&](int i) { mbar_wait(bars_s + 8 * (uint32_t)(i & (kBulkRing - 1)), (uint32_t)(i / kBulkRing) & 1u); };
+    auto wait_stage = [&](int k) { mbar_wait(bars_s + 8 * (uint32_t)(k & (kStages - 1)), (uint32_t)(k / kStages) & 1u); };
     if (lane == 0) {
 #pragma unroll 1
-        for (int i = 0; i < kBulkRing; ++i) issue(i);
+        for (int k = 0; k < kStages; ++k) issue_stage(k);
     }
 
     // REFLECT_101 at the right image edge: columns w, w+1 mirror w-2, w-3; patched inside the landed slot by two
     // lanes (the sources are always inside the slot: body or left halo).  The left edge is fixed in registers.
-    const bool fix_right = (w < X0 + BC::BODY + 4);
+    const bool fix_right = (w < X0 + BODY + 4);
     const int fr_c = w - X0 + lane;                  // lane 0: column w (mirror: -2), lane 1: column w+1 (mirror: -4)
-    const bool fr_on = (lane < 2) && (fr_c < BC::BODY + 4);
+    const bool fr_on = (lane < 2) && (fr_c < BODY + 4);
     const uint32_t fr_dst = ring_s + 16 + fr_c, fr_src = fr_dst - 2 - 2 * lane;
     const bool fix_left = (X0 == 0) && (lane == 0);
     auto patch_right = [&](int i) {
-        const uint32_t so = (uint32_t)(i & (kBulkRing - 1)) * BC::SLOT;
+        const uint32_t so = (uint32_t)(i & (kTmaRing - 1)) * SLOT;
         if (fr_on) sts_u8(fr_dst + so, lds_u8(fr_src + so));
     };
     // Words of one landed row: W[0] = the 4 bytes left of the own bytes, W[1..NW] = own bytes, W[NW+1] = the 4 bytes right.
     auto load_row = [&](int i, uint32_t (&W)[NW + 2]) {
-        const uint32_t a = my_s + (uint32_t)(i & (kBulkRing - 1)) * BC::SLOT;
+        const uint32_t a = my_s + (uint32_t)(i & (kTmaRing - 1)) * SLOT;
         if constexpr (NOUT == 8) {
             const uint4 v = lds_v4(a);
             W[1] = v.x; W[2] = v.y; W[3] = v.z; W[4] = v.w;
@@ -577,12 +576,12 @@ pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
         (OUT_)[2 * k_ + 1] = dp4a_uu((W_)[k_ + 1], 0x04060401u * (M_), dp4a_uu((W_)[k_ + 2], 0x00000001u * (M_), (INIT_)[2 * k_ + 1])); \
     }
 
-    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r), see pyr_down_ring_kernel:
+    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r), see ring_task:
     //   E_y = h_{2y} + 16,  P_y = E_y + 4 h_{2y+1},  V_y = P_{y-1} + P_y + 5 E_y + E_{y+1},  dst = V_y >> 8
     uint32_t e_cur[NOUT], p_prev[NOUT], k16[NOUT];
 #pragma unroll
     for (int i = 0; i < NOUT; ++i) k16[i] = 16u;
-    wait_row(0); wait_row(1); wait_row(2);
+    wait_stage(0);
     if (fix_right) {      // warp-uniform
         patch_right(0); patch_right(1); patch_right(2);
         __syncwarp();
@@ -596,27 +595,23 @@ pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
         KLT_HORIZ(wb, 4u, e_m1, p_prev);
         KLT_HORIZ(wc, 1u, k16, e_cur);
     }
-    __syncwarp();   // every lane has read rows 0..2: slot 0 may be refilled
-    if (lane == 0) {
-        if (fix_right) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(kBulkRing);
-    }
     const int xo = cb >> 1;
-    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
+    uint8_t* __restrict__ drow = dimg + (long long)y0 * dpitch + xo;
     const bool full_store = (xo + NOUT <= dw);
 
-#pragma unroll 2
-    for (int t = 0; t < n_out; ++t) {
-        // rows <= 2t+2 were read by every lane in earlier iterations: their slots take rows 2t+1+R, 2t+2+R
-        __syncwarp();
-        if (lane == 0) {
-            if (fix_right) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(2 * t + 1 + kBulkRing);
-            issue(2 * t + 2 + kBulkRing);
+    auto step = [&](int t, auto odd_tag, auto fix_tag) {
+        constexpr bool ODD = decltype(odd_tag)::value, FIX = decltype(fix_tag)::value;
+        if (ODD) {
+            // step t-1 read the last row of stage (t-1)/2; every lane is past it after this barrier: refill its buffer
+            __syncwarp();
+            if (lane == 0) {
+                if (FIX) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_stage((t >> 1) + kStages);
+            }
+        } else {
+            wait_stage((t >> 1) + 1);   // row 2t+4 opens stage t/2 + 1 (row 2t+3 closes stage t/2, already waited for)
         }
-        wait_row(2 * t + 3);
-        wait_row(2 * t + 4);
-        if (fix_right) {
+        if (FIX) {
             patch_right(2 * t + 3); patch_right(2 * t + 4);
             __syncwarp();
         }
@@ -648,241 +643,109 @@ pyr_down_bulk_kernel(const uint8_t* __restrict__ src, int w, int h, long long sp
                 if (xo + i < dw) drow[i] = (uint8_t)(v[i] >> 8);
         }
         drow += dpitch;
-    }
+    };
+    auto body = [&](auto fix_tag) {
+        int t = 0;
+        for (; t + 1 < n_out; t += 2) {
+            step(t, std::false_type{}, fix_tag);
+            step(t + 1, std::true_type{}, fix_tag);
+        }
+        if (t < n_out) step(t, std::false_type{}, fix_tag);
+    };
+    // the right-edge patch is needed by the last tile of a row only: keep it (and its warp barrier) out of the others
+    if (fix_right) body(std::true_type{}); else body(std::false_type{});
 #undef KLT_HORIZ
 }
 
-// ---------------------------------------------------------------------------------------------------
-// cp.async ring with run-time slot indexing and a template ring depth (RING rows per warp, RING - 4 of them in flight).
-template <int NOUT, int RING, int MINB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
-pyr_down_ring2_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, long long sbatch,
-                      uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
-                      int rows_per_strip, int tiles_x, int strips_y, long long n_tasks)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+pyr_down_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ src, int w, int h, long long spitch,
+                    long long sbatch, uint8_t* __restrict__ dst, int dw, int dh, long long dpitch, long long dbatch,
+                    int rows_per_strip, int tiles_x, int n8, int rem_nout, int strips_y, long long n_tasks)
 {
-    constexpr int BODY = 64 * NOUT, SLOT = BODY + 32, NW = NOUT / 2;
-    static_assert((RING & (RING - 1)) == 0 && RING >= 8, "ring depth must be a power of two");
     extern __shared__ __align__(128) uint8_t ring_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
     if (task >= n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
-
     const int tx = (int)(task % tiles_x);
     const long long t2 = task / tiles_x;
     const int sy = (int)(t2 % strips_y);
     const int b = (int)(t2 / strips_y);
     const uint8_t* __restrict__ simg = src + (long long)b * sbatch;
-
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RING * SLOT);
-    const int X0 = tx * BODY;                     // first input column of the tile
-    const int cb = X0 + 2 * NOUT * lane;          // first own input column
+    uint8_t* __restrict__ dimg = dst + (long long)b * dbatch;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * kTmaWarpBytes);
+    const int X0 = tx * 512;
     const int y0 = sy * rows_per_strip;
     const int y1 = min(y0 + rows_per_strip, dh);
-    const int n_out = y1 - y0;
-    const int n_rows = 2 * n_out + 3;             // input rows 2*y0-2 .. 2*y1
-    const uint32_t my_s = ring_s + 16 + 2 * NOUT * lane;   // own bytes inside slot 0
-    const uint8_t* __restrict__ gown = simg + cb;
-    // one extra 4-byte halo copy per row: lane 0 fetches columns X0-4..X0-1, lane 31 columns X0+BODY..X0+BODY+3
-    const bool has_x = (lane == 0 && X0 > 0) || (lane == 31 && X0 + BODY < w);
-    const uint32_t x_s = ring_s + ((lane == 0) ? 12u : (uint32_t)(16 + BODY));
-    const uint8_t* __restrict__ gx = simg + ((lane == 0) ? (X0 - 4) : (X0 + BODY));
-    const int hm2 = 2 * h - 2;
-    const unsigned pitch32 = (unsigned)spitch;    // h * pitch < 2^31 is checked by the launcher
-    const int r_first = 2 * y0 - 2;
-    const bool do_own = cb < w;
-
-    // input row i of the strip = image row 2*y0-2+i under REFLECT_101 (min(|r|, 2h-2-|r|) for -h < r < 2h-1), slot i % RING.
-    // Copies are whole 16/8/4-byte granules: a granule that holds at least one pixel lies inside the 16-byte-pitched row,
-    // and the bytes past column w-1 it may bring along are never used.  One commit group per row, always.
-    auto issue = [&](int i) {
-        if (i < n_rows) {   // warp-uniform
-            const int ra = abs(r_first + i);
-            const unsigned long long off = (unsigned long long)(unsigned)min(ra, hm2 - ra) * pitch32;
-            const uint32_t so = (uint32_t)(i & (RING - 1)) * SLOT;
-            if (do_own) {
-                if constexpr (NOUT == 8) cp_async_16(my_s + so, gown + off);
-                else cp_async_8(my_s + so, gown + off);
-            }
-            if (has_x) cp_async_4(x_s + so, gx + off);
-        }
-        cp_async_commit();
-    };
-    const bool fix_right = (w < X0 + BODY + 4);
-    const int fr_c = w - X0 + lane;                  // lane 0: column w (mirror: -2), lane 1: column w+1 (mirror: -4)
-    const bool fr_on = (lane < 2) && (fr_c < BODY + 4);
-    const uint32_t fr_dst = ring_s + 16 + fr_c, fr_src = fr_dst - 2 - 2 * lane;
-    const bool fix_left = (X0 == 0) && (lane == 0);
-    auto patch_right = [&](int i) {
-        const uint32_t so = (uint32_t)(i & (RING - 1)) * SLOT;
-        if (fr_on) sts_u8(fr_dst + so, lds_u8(fr_src + so));
-    };
-    auto load_row = [&](int i, uint32_t (&W)[NW + 2]) {
-        const uint32_t a = my_s + (uint32_t)(i & (RING - 1)) * SLOT;
-        if constexpr (NOUT == 8) {
-            const uint4 v = lds_v4(a);
-            W[1] = v.x; W[2] = v.y; W[3] = v.z; W[4] = v.w;
-        } else {
-            const uint2 v = lds_v2(a);
-            W[1] = v.x; W[2] = v.y;
-        }
-        W[0] = lds_u32(a - 4);
-        W[NW + 1] = lds_u32(a + 2 * NOUT);
-        if (fix_left) W[0] = prmt(W[1], W[1], 0x1200u);   // columns -2,-1 mirror 2,1
-    };
-#define KLT_HORIZ(W_, M_, INIT_, OUT_)                                                                  \
-    _Pragma("unroll") for (int k_ = 0; k_ < NW; ++k_) {                                                 \
-        (OUT_)[2 * k_] = dp4a_uu((W_)[k_], 0x04010000u * (M_), dp4a_uu((W_)[k_ + 1], 0x00010406u * (M_), (INIT_)[2 * k_]));          \
-        (OUT_)[2 * k_ + 1] = dp4a_uu((W_)[k_ + 1], 0x04060401u * (M_), dp4a_uu((W_)[k_ + 2], 0x00000001u * (M_), (INIT_)[2 * k_ + 1])); \
-    }
-
-#pragma unroll
-    for (int i = 0; i < RING - 1; ++i) issue(i);
-    cp_async_wait<RING - 4>();   // rows 0, 1, 2 have landed
-    __syncwarp();
-    if (fix_right) {             // warp-uniform
-        patch_right(0); patch_right(1); patch_right(2);
-        __syncwarp();
-    }
-    // Vertical pass as a recurrence over output rows y (h_r = horizontal sum of input row r):
-    //   E_y = h_{2y} + 16,  P_y = E_y + 4 h_{2y+1},  V_y = P_{y-1} + P_y + 5 E_y + E_{y+1}
-    //       = h_{2y-2} + 4 h_{2y-1} + 6 h_{2y} + 4 h_{2y+1} + h_{2y+2} + 128;   dst = V_y >> 8   (V_y <= 65408)
-    // Every input row gets exactly one horizontal pass; the x4 of the odd rows is folded into the dp4a coefficients.
-    uint32_t e_cur[NOUT], p_prev[NOUT], k16[NOUT];
-#pragma unroll
-    for (int i = 0; i < NOUT; ++i) k16[i] = 16u;
-    {
-        uint32_t wa[NW + 2], wb[NW + 2], wc[NW + 2], e_m1[NOUT];
-        load_row(0, wa);
-        load_row(1, wb);
-        load_row(2, wc);
-        KLT_HORIZ(wa, 1u, k16, e_m1);
-        KLT_HORIZ(wb, 4u, e_m1, p_prev);
-        KLT_HORIZ(wc, 1u, k16, e_cur);
-    }
-    const int xo = cb >> 1;
-    uint8_t* __restrict__ drow = dst + (long long)b * dbatch + (long long)y0 * dpitch + xo;
-    const bool full_store = (xo + NOUT <= dw);
-
-    auto body = [&](auto fix_tag) {
-        constexpr bool FIX = decltype(fix_tag)::value;
-#pragma unroll 2
-        for (int t = 0; t < n_out; ++t) {
-            cp_async_wait<RING - 6>();   // rows <= 2t+4 have landed; the newest RING-6 groups may still be in flight
-            __syncwarp();
-            if (FIX) {
-                patch_right(2 * t + 3); patch_right(2 * t + 4);
-                __syncwarp();
-            }
-            uint32_t wo[NW + 2], we[NW + 2];
-            load_row(2 * t + 3, wo);
-            load_row(2 * t + 4, we);
-            // rows 2t-1, 2t were last read one iteration ago (all lanes passed the barrier above): refill their slots
-            issue(2 * t + RING - 1);
-            issue(2 * t + RING);
-            uint32_t p_cur[NOUT], e_nxt[NOUT], v[NOUT];
-            KLT_HORIZ(wo, 4u, e_cur, p_cur);
-            KLT_HORIZ(we, 1u, k16, e_nxt);
-#pragma unroll
-            for (int i = 0; i < NOUT; ++i) {
-                v[i] = (5u * e_cur[i] + p_cur[i]) + (p_prev[i] + e_nxt[i]);
-                p_prev[i] = p_cur[i];
-                e_cur[i] = e_nxt[i];
-            }
-            if (full_store) {
-                // byte 1 of every V: pair two V's into one word (V < 2^16), then one PRMT per 4 outputs
-                if constexpr (NOUT == 8) {
-                    uint2 o;
-                    o.x = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
-                    o.y = prmt(v[5] * 65536u + v[4], v[7] * 65536u + v[6], 0x7531u);
-                    *reinterpret_cast<uint2*>(drow) = o;
-                } else {
-                    *reinterpret_cast<uint32_t*>(drow) = prmt(v[1] * 65536u + v[0], v[3] * 65536u + v[2], 0x7531u);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NOUT; ++i)
-                    if (xo + i < dw) drow[i] = (uint8_t)(v[i] >> 8);
-            }
-            drow += dpitch;
-        }
-    };
-    // the right-edge patch is needed by the last tile of a row only: keep it (and its warp barrier) out of the others
-    if (fix_right) body(std::true_type{}); else body(std::false_type{});
-    cp_async_wait<0>();
-#undef KLT_HORIZ
+    if (tx < n8 || rem_nout == 8) tma_task<8>(&tmap, simg, b, w, h, spitch, dimg, dw, dpitch, X0, y0, y1, ring_s, lane);
+    else tma_task<4>(&tmap, simg, b, w, h, spitch, dimg, dw, dpitch, X0, y0, y1, ring_s, lane);
 }
 
-template <int NOUT, int RING, int MINB>
-klt_status launch_ring2(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
-                        int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+klt_status launch_tma(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
+                      int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
 {
     static bool configured = false;
-    const int smem = RING * (64 * NOUT + 32) * kWarpsPerBlock;
+    const int smem = kTmaWarpBytes * kWarpsPerBlock;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring2_kernel<NOUT, RING, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
         configured = true;
     }
-    const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
-    const long long resident = (long long)sm_count * MINB * kWarpsPerBlock;
-    int rows = 2;
-    double best = 1e300;
-    for (int r = 2; r <= 64; ++r) {
-        const int strips = (dh + r - 1) / r;
-        const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
-        const long long tasks = (long long)tiles_x * strips * batch;
-        const long long rounds = (tasks + resident - 1) / resident;
-        const double cost = (double)rounds * (2.0 * rr + 3.0 + 6.0);
-        if (cost < best) { best = cost; rows = rr; }
-    }
-    const int strips_y = (dh + rows - 1) / rows;
-    const long long n_tasks = (long long)tiles_x * strips_y * batch;
-    const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_down_ring2_kernel<NOUT, RING, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
-        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? KLT_OK : (klt_status)e;
-}
-
-template <int NOUT>
-klt_status launch_bulk(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
-                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
-{
-    using BC = BulkCfg<NOUT>;
-    static bool configured = false;
-    const int smem = BC::WARP_BYTES * kWarpsPerBlock;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_down_bulk_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (klt_status)e;
-        configured = true;
-    }
-    const int tiles_x = (dw + 32 * NOUT - 1) / (32 * NOUT);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return KLT_ERR_INTERNAL;
+    // the image batch as a (pitch/4, h, batch) tensor of 32-bit words: boxes are 136 words x kRowsPerStage rows
+    CUtensorMap tmap;
+    const long long bstride = (batch > 1) ? sbatch : spitch * h;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(spitch / 4), (cuuint64_t)h, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)spitch, (cuuint64_t)bstride};
+    const cuuint32_t box[3] = {(cuuint32_t)(kTmaSlot / 4), (cuuint32_t)kRowsPerStage, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return KLT_ERR_INTERNAL;
+    const int n8 = w / 512, rem = w - n8 * 512;
+    const int rem_nout = (rem == 0) ? 0 : (rem <= 256 ? 4 : 8);
+    const int tiles_x = n8 + (rem > 0);
     // Strip height: a warp task costs about (2*rows + 3 input rows + pipeline fill); tasks run in rounds of `resident`
-    // warps (3 CTAs of 8 warps per SM).  Pick the height that minimises rounds x task cost -- tall strips amortise the
-    // 3 halo rows and the fill, but a nearly empty last round is pure loss.
+    // warps (3 CTAs of 8 warps per SM).  Pick the height that minimises rounds x task cost.
     const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
     int rows = 2;
     double best = 1e300;
-    for (int r = 2; r <= 64; ++r) {
+    for (int r = 2; r <= 48; ++r) {
         const int strips = (dh + r - 1) / r;
         const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
         const long long tasks = (long long)tiles_x * strips * batch;
         const long long rounds = (tasks + resident - 1) / resident;
-        const double cost = (double)rounds * (2.0 * rr + 3.0 + 10.0);
+        const double cost = (double)rounds * (2.0 * rr + 3.0 + 8.0);
         if (cost < best) { best = cost; rows = rr; }
     }
     const int strips_y = (dh + rows - 1) / rows;
     const long long n_tasks = (long long)tiles_x * strips_y * batch;
     const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_down_bulk_kernel<NOUT><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
-        src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, strips_y, n_tasks);
+    pyr_down_tma_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+        tmap, src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, n8, rem_nout, strips_y, n_tasks);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
+template <int MINB>
 klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
                        int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
 {
@@ -890,7 +753,7 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
     static bool configured = false;
     const int smem = RC::WARP_BYTES * kWarpsPerBlock;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
         configured = true;
     }
@@ -900,7 +763,7 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
     // Strip height: every warp task costs about (2*rows + 3 input rows + pipeline fill); tasks run in rounds of
     // `resident` warps (3 CTAs of 8 warps per SM at 80 registers).  Pick the height that minimises
     // rounds x task cost -- tall strips amortise the 3 halo rows, but a nearly empty last round is pure loss.
-    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
+    const long long resident = (long long)sm_count * MINB * kWarpsPerBlock;
     int rows = 2;
     double best = 1e300;
     for (int r = 2; r <= 48; ++r) {
@@ -911,11 +774,13 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
         const double cost = (double)rounds * (2.0 * rr + 3.0 + 6.0);
         if (cost < best) { best = cost; rows = rr; }
     }
+    static const char* force_rows = getenv("KLT_PYR_ROWS");   // tuning aid
+    if (force_rows && atoi(force_rows) >= 2) rows = min(atoi(force_rows), dh);
     const int strips_y = (dh + rows - 1) / rows;
     const long long n_tasks = (long long)tiles_x * strips_y * batch;
     const long long blocks = (n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_down_ring_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
+    pyr_down_ring_kernel<MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(
         src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, rows, tiles_x, n8, rem_nout, strips_y, n_tasks);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
@@ -995,17 +860,12 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
     const bool use8 = (t8 * 3 <= dw * 4) || (t8 == t4);
     static const char* force_fallback = getenv("KLT_PYR_FALLBACK");   // tests: exercise the shuffle/gather kernel
     if (aligned && w >= 4 && h >= 3 && (long long)h * spitch < 0x7fffffffLL && !(force_fallback && force_fallback[0] == '1')) {
-        static const char* force_ring = getenv("KLT_PYR_RING");   // A/B between the load paths
-        const char fr = force_ring ? force_ring[0] : '1';
-        if (fr == '2')
-            return use8 ? launch_ring2<8, 16, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
-                        : launch_ring2<4, 16, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
-        if (fr == '3')
-            return use8 ? launch_ring2<8, 8, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
-                        : launch_ring2<4, 8, 3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
-        if (fr == '1') return launch_ring(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
-        return use8 ? launch_bulk<8>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
-                    : launch_bulk<4>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        // Measured on B200 (profiles/): the cp.async ring reaches 55-66 % of the copy peak; the TMA variant
+        // (same math, UTMALDG boxes of 4 rows) 36-51 % -- so the ring is the product path and KLT_PYR_TMA=1 selects the
+        // TMA kernel for A/B runs only.
+        static const char* force_tma = getenv("KLT_PYR_TMA");
+        if (force_tma && force_tma[0] == '1') return launch_tma(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        return launch_ring<3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
     }
     if (aligned) {
         return use8 ? launch_t<8, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
