@@ -354,6 +354,8 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
     for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
 
     const long long t_start = clock64();
+    unsigned gt_start = 0;
+    if (L.flags & 0x200) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(gt_start));
     int n_t1 = 0, n_t2 = 0;
     const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
     float2 outp = make_float2(0.f, 0.f);
@@ -371,6 +373,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
         const int lw = lvI.w, lh = lvI.h;
         const float scale = __int_as_float((127 - level) << 23);
+        const int it_inc = (L.flags & 0x400) ? (1 << (8 * (level & 3))) : 1;   // debug flag 0x400: per-level counts, 8 bits each
 
         float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
         float nx, ny;
@@ -618,7 +621,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 if (level == 0) status = 0;
                 break;
             }
-            ++iters;
+            iters += it_inc;
             ensure_j(inx, iny);
             int v00, v01, v10, v11;
             q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
@@ -794,7 +797,11 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         L.err[gid] = err;
         if (L.iters) {
             // debug flag 0x100: cycles / 64 in the low 20 bits, tier-1 and tier-2 counts above (profiling aid)
-            L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
+            // debug flag 0x200: start time (globaltimer ns / 32, low 16 bits) | duration (ns / 32) << 16
+            unsigned gt_end = 0;
+            if (L.flags & 0x200) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(gt_end));
+            if (L.flags & 0x200) L.iters[gid] = (int)(((gt_start >> 5) & 0xffffu) | (min((gt_end - gt_start) >> 5, 0xffffu) << 16));
+            else L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
         }
     }
 }
