@@ -5,7 +5,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libklt_b200.so")
+LIB_PATH = os.environ.get("KLT_LIB_PATH") or os.path.join(_PKG, "lib", "libklt_b200.so")   # override: A/B runs of another build
 
 KLT_MAX_LEVELS = 16
 KLT_MAX_WIN_AREA = 4096

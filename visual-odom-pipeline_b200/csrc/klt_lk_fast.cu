@@ -35,22 +35,18 @@ __host__ __device__ constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 template <int WW, int WH>
 struct Chains {
     static constexpr int NV = 8 * (WW / 8), TL = WW - NV;
-    // G: one element per pixel
+    // G scratch: 12 SIMD chains (3 sums x 4 lanes, one float product per pixel) of GQ4 floats, then 3 tail chains of
+    // GT4 floats (zero padded to multiples of 4), then 16 result words
     static constexpr int GQ = WH * (NV / 4), GT = WH * TL;
-    static constexpr int GLEN = (GQ > GT ? GQ : GT);                 // padded chain length (words)
-    static constexpr int G_WORDS = 5 * GLEN;
-    // b: SIMD lanes consume (x, x+4) pairs, the tail single pixels; both stored as ints, two per step
-    static constexpr int BQ = 2 * WH * (NV / 8), BT = WH * TL;
-    static constexpr int BLEN = ((BQ > BT ? BQ : BT) + 1) / 2 * 2;   // padded chain length (ints, even)
-    static constexpr int B_WORDS = 10 * BLEN;
-    __device__ static __forceinline__ int slot_g(int y, int x)
-    {
-        return (x < NV) ? ((x & 3) * GLEN + y * (NV / 4) + (x >> 2)) : (4 * GLEN + y * TL + (x - NV));
-    }
-    __device__ static __forceinline__ int slot_b(int y, int x)   // within one sum (add 5 * BLEN for the second)
-    {
-        return (x < NV) ? ((x & 3) * BLEN + (y * (NV / 8) + (x >> 3)) * 2 + ((x >> 2) & 1)) : (4 * BLEN + y * TL + (x - NV));
-    }
+    static constexpr int GQ4 = (GQ + 3) / 4 * 4, GT4 = (GT + 3) / 4 * 4;
+    static constexpr int G_RES = 12 * GQ4 + 3 * GT4;
+    static constexpr int G_WORDS = G_RES + 16;
+    // b scratch: 8 SIMD chains (2 sums x 4 lanes) of int pairs (x, x+4) in visiting order, then 2 tail chains of floats
+    static constexpr int NS = NV / 8;                                // 8-pixel SIMD steps per window row
+    static constexpr int SLEN = 2 * WH * NS;                         // ints per SIMD chain
+    static constexpr int TLEN = (WH * TL + 3) / 4 * 4;               // floats per tail chain (zero padded)
+    static constexpr int B_RES = 8 * SLEN + 2 * TLEN;                // 12 result words: q[0..3] of b1, of b2, t of b1, of b2
+    static constexpr int B_WORDS = (B_RES + 12 + 3) / 4 * 4;
 };
 
 template <int WW, int WH, int WPP>
@@ -75,7 +71,7 @@ struct Cfg {
     // shared-memory slice of one point (bytes)
     static constexpr int OFF_J = 0;
     static constexpr int OFF_D = OFF_J + r16(SJ * JR);        // dreg; fallback: packed derivative patch
-    static constexpr int CHAIN_WORDS = Chains<WW, WH>::B_WORDS > Chains<WW, WH>::G_WORDS ? Chains<WW, WH>::B_WORDS : Chains<WW, WH>::G_WORDS;
+    static constexpr int CHAIN_WORDS = r4(Chains<WW, WH>::B_WORDS > Chains<WW, WH>::G_WORDS ? Chains<WW, WH>::B_WORDS : Chains<WW, WH>::G_WORDS);   // replay scratch
     static constexpr int D_BYTES = r16(4 * (SD * DR > CHAIN_WORDS ? SD * DR : CHAIN_WORDS));  // dreg, or the replay chains
     static constexpr int OFF_I = OFF_D + D_BYTES;             // ireg
     static constexpr int I_BYTES = r16(SI * IR);
@@ -251,73 +247,72 @@ __device__ __forceinline__ int point_sum15_lane(const int (&v)[16], int* red16, 
     return mine;
 }
 
-// zero the padding of the chain rows (NT threads of one point)
-template <int WW, int WH, int NT>
-__device__ __forceinline__ void zero_pad_g(uint32_t* pat, int tid)
+// serial float32 sum of one zero-padded chain of n4 floats (n4 % 4 == 0), in order
+__device__ __forceinline__ float chain_sum(const float* __restrict__ p, int n4)
 {
-    using CH = Chains<WW, WH>;
-    constexpr int PQ = CH::GLEN - CH::GQ, PT = CH::GLEN - CH::GT;
-    for (int i = tid; i < 4 * PQ + PT; i += NT) {
-        const int k = (i < 4 * PQ) ? i / (PQ > 0 ? PQ : 1) : 4;
-        const int o = (i < 4 * PQ) ? i - k * PQ : i - 4 * PQ;
-        pat[k * CH::GLEN + (k < 4 ? CH::GQ : CH::GT) + o] = 0u;
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(p);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < n4 / 4; ++e) {
+        const float4 v = src[e];
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
     }
+    return acc;
 }
-template <int WW, int WH, int NT>
-__device__ __forceinline__ void zero_pad_b(int* prod, int tid)
+
+// G replay, split over the point's warps: warp 0 runs the 12 SIMD chains (lane = chain), warp TW the 3 tail chains.
+// The products were converted to float by the threads that own the pixels (|gx*gy| < 2^24: exact).
+template <int WW, int WH, int WPP>
+__device__ __forceinline__ void replay_g(float* __restrict__ gf, int wip, int lane)
 {
     using CH = Chains<WW, WH>;
-    constexpr int PQ = CH::BLEN - CH::BQ, PT = CH::BLEN - CH::BT;
-    for (int i = tid; i < 2 * (4 * PQ + PT); i += NT) {
-        const int s = i / (4 * PQ + PT), r = i - s * (4 * PQ + PT);
-        const int k = (r < 4 * PQ) ? r / (PQ > 0 ? PQ : 1) : 4;
-        const int o = (r < 4 * PQ) ? r - k * PQ : r - 4 * PQ;
-        prod[(s * 5 + k) * CH::BLEN + (k < 4 ? CH::BQ : CH::BT) + o] = 0;
+    constexpr int TW = WPP > 1 ? 1 : 0;
+    if (wip == 0) {
+        const float acc = chain_sum(gf + (lane < 12 ? lane : 0) * CH::GQ4, CH::GQ4);
+        if (lane < 12) gf[CH::G_RES + (lane >> 2) * 5 + (lane & 3)] = acc;   // result layout: [sum][q0 q1 q2 q3 t]
+    }
+    if (wip == TW) {
+        const float acc = chain_sum(gf + 12 * CH::GQ4 + (lane < 3 ? lane : 0) * CH::GT4, CH::GT4);
+        if (lane < 3) gf[CH::G_RES + lane * 5 + 4] = acc;
     }
 }
 
-// G: lanes 0..14 of ONE warp = 3 sums x (4 SIMD lanes + tail); scratch rows hold packed (gx | gy << 16) words
-template <int WW, int WH>
-__device__ __forceinline__ void replay_g(const uint32_t* __restrict__ pat, int lane, float& A11, float& A12, float& A22)
+// zero the padding of the two tail chains of one b scratch buffer
+template <int WW, int WH, int NT>
+__device__ __forceinline__ void zero_pad_b(int* buf, int tid)
 {
     using CH = Chains<WW, WH>;
-    const int s = (lane < 15) ? lane / 5 : 0, k = (lane < 15) ? lane - 5 * (lane / 5) : 0;
-    const uint32_t* __restrict__ src = pat + k * CH::GLEN;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < CH::GLEN; ++e) {
-        const uint32_t wd = src[e];
-        const int gx = lo16(wd), gy = hi16(wd);
-        const int prod = ((s == 0) ? gx : gy) * ((s == 2) ? gy : gx);   // gx*gx, gy*gx, gy*gy
-        acc = __fadd_rn(acc, (float)prod);
-    }
-    float r[3];
-#pragma unroll
-    for (int ss = 0; ss < 3; ++ss)
-        r[ss] = combine5(__shfl_sync(kFull, acc, 5 * ss), __shfl_sync(kFull, acc, 5 * ss + 1), __shfl_sync(kFull, acc, 5 * ss + 2),
-                         __shfl_sync(kFull, acc, 5 * ss + 3), __shfl_sync(kFull, acc, 5 * ss + 4));
-    A11 = r[0]; A12 = r[1]; A22 = r[2];
+    constexpr int PAD = CH::TLEN - WH * CH::TL;
+    if (tid < 2 * PAD) buf[8 * CH::SLEN + (tid / (PAD > 0 ? PAD : 1)) * CH::TLEN + WH * CH::TL + tid % (PAD > 0 ? PAD : 1)] = 0;
 }
 
-// b: lanes 0..9 of ONE warp = 2 sums x (4 SIMD lanes + tail); scratch rows hold the integer products d*g
-template <int WW, int WH>
-__device__ __forceinline__ void replay_b(const int* __restrict__ prod, int lane, float& b1, float& b2)
+// b replay, split over the point's warps: warp 0 runs the 8 SIMD chains (lane = chain; int pair -> float -> add), warp
+// TW the 2 tail chains (floats, converted by the threads that own the pixels).  Results go to buf[B_RES ..].
+template <int WW, int WH, int WPP>
+__device__ __forceinline__ void replay_b(int* __restrict__ buf, int wip, int lane)
 {
     using CH = Chains<WW, WH>;
-    const int c = (lane < 10) ? lane : 0;
-    const int pairmask = ((c % 5) < 4) ? -1 : 0;   // SIMD lanes add the two halves of a pair in int32 first
-    const int2* __restrict__ src = reinterpret_cast<const int2*>(prod + c * CH::BLEN);
-    float acc = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < CH::BLEN / 2; ++e) {
-        const int2 v = src[e];
-        acc = __fadd_rn(acc, (float)(v.x + (v.y & pairmask)));
-        acc = __fadd_rn(acc, (float)(v.y & ~pairmask));
+    constexpr int TW = WPP > 1 ? 1 : 0;
+    if (wip == 0) {
+        const int2* __restrict__ src = reinterpret_cast<const int2*>(buf + (lane & 7) * CH::SLEN);
+        float acc = 0.f;
+#pragma unroll 6
+        for (int e = 0; e < CH::SLEN / 2; ++e) {
+            const int2 v = src[e];
+            acc = __fadd_rn(acc, (float)(v.x + v.y));
+        }
+        if (lane < 8) reinterpret_cast<float*>(buf)[CH::B_RES + lane] = acc;
     }
-    b1 = combine5(__shfl_sync(kFull, acc, 0), __shfl_sync(kFull, acc, 1), __shfl_sync(kFull, acc, 2), __shfl_sync(kFull, acc, 3),
-                  __shfl_sync(kFull, acc, 4));
-    b2 = combine5(__shfl_sync(kFull, acc, 5), __shfl_sync(kFull, acc, 6), __shfl_sync(kFull, acc, 7), __shfl_sync(kFull, acc, 8),
-                  __shfl_sync(kFull, acc, 9));
+    if (wip == TW) {
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(buf + 8 * CH::SLEN + (lane & 1) * CH::TLEN);
+        float acc = 0.f;
+#pragma unroll 4
+        for (int e = 0; e < CH::TLEN / 4; ++e) {
+            const float4 v = src[e];
+            acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+        }
+        if (lane < 2) reinterpret_cast<float*>(buf)[CH::B_RES + 8 + lane] = acc;
+    }
 }
 
 template <int WW, int WH, int WPP>
@@ -354,8 +349,6 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
     for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
 
     const long long t_start = clock64();
-    unsigned gt_start = 0;
-    if (L.flags & 0x200) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(gt_start));
     int n_t1 = 0, n_t2 = 0;
     const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
     float2 outp = make_float2(0.f, 0.f);
@@ -373,7 +366,6 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
         const int lw = lvI.w, lh = lvI.h;
         const float scale = __int_as_float((127 - level) << 23);
-        const int it_inc = (L.flags & 0x400) ? (1 << (8 * (level & 3))) : 1;   // debug flag 0x400: per-level counts, 8 bits each
 
         float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
         float nx, ny;
@@ -575,20 +567,39 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 A22 = combine5(__shfl_sync(kFull, f, 10), __shfl_sync(kFull, f, 11), __shfl_sync(kFull, f, 12), __shfl_sync(kFull, f, 13),
                                __shfl_sync(kFull, f, 14));
             } else {
-                // serial replay in OpenCV's order (A.5) from a chain-ordered smem copy of the derivative patch
-                uint32_t* dpat = dreg;  // dreg is dead (every warp passed the exchange barrier above)
+                // serial replay in OpenCV's order (A.5): every thread stores the float products of its pixels in chain
+                // order; all scratch is dead here (every warp passed the exchange barrier above)
+                using CH = Chains<WW, WH>;
+                float* gf = reinterpret_cast<float*>(dreg);
 #pragma unroll
                 for (int k = 0; k < C::UPT; ++k)
                     if (unit_ok(k)) {
+                        const int y = unit_y(k), x0 = unit_x0(k);
+                        const bool tail = x0 >= C::NV;
+                        float* g0 = tail ? gf + 12 * CH::GQ4 + y * CH::TL + (x0 - C::NV) : gf + y * (C::NV / 4) + (x0 >> 2);
+                        const int sj = tail ? 1 : CH::GQ4;            // next pixel: next element of the tail / next lane chain
+                        const int ss = tail ? CH::GT4 : 4 * CH::GQ4;  // next sum
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (unit_x0(k) + j < WW)
-                                dpat[Chains<WW, WH>::slot_g(unit_y(k), unit_x0(k) + j)] =
-                                    ((uint32_t)pxs[k][j].gx() & 0xffffu) | ((uint32_t)pxs[k][j].gy() << 16);
+                            if (x0 + j < WW) {
+                                const int gx = pxs[k][j].gx(), gy = pxs[k][j].gy();
+                                g0[j * sj] = (float)(gx * gx);
+                                g0[j * sj + ss] = (float)(gx * gy);
+                                g0[j * sj + 2 * ss] = (float)(gy * gy);
+                            }
                     }
-                zero_pad_g<WW, WH, C::NT>(dpat, tid);
+                {   // zero pads
+                    constexpr int PQ = CH::GQ4 - CH::GQ, PT = CH::GT4 - CH::GT;
+                    if (tid < 12 * PQ) gf[(tid / (PQ > 0 ? PQ : 1)) * CH::GQ4 + CH::GQ + tid % (PQ > 0 ? PQ : 1)] = 0.f;
+                    if (tid < 3 * PT) gf[12 * CH::GQ4 + (tid / (PT > 0 ? PT : 1)) * CH::GT4 + CH::GT + tid % (PT > 0 ? PT : 1)] = 0.f;
+                }
                 point_sync<WPP>(bar);
-                replay_g<WW, WH>(dpat, lane, A11, A12, A22);  // every warp of the point computes the same values
+                replay_g<WW, WH, WPP>(gf, wip, lane);
+                point_sync<WPP>(bar);
+                const float* r = gf + CH::G_RES;
+                A11 = combine5(r[0], r[1], r[2], r[3], r[4]);
+                A12 = combine5(r[5], r[6], r[7], r[8], r[9]);
+                A22 = combine5(r[10], r[11], r[12], r[13], r[14]);
             }
         }
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -621,7 +632,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 if (level == 0) status = 0;
                 break;
             }
-            iters += it_inc;
+            ++iters;
             ensure_j(inx, iny);
             int v00, v01, v10, v11;
             q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
@@ -715,25 +726,44 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     b2 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
                                   __shfl_sync(kFull, f, 9));
                 } else {
-                    // tier 2: serial replay (pairs (l, l+4) summed in int32 first; A.5)
+                    // tier 2: serial replay (pairs (l, l+4) summed in int32 first; A.5).  The scratch is rewritten by the
+                    // next replay only after every warp has passed that replay's first barrier, i.e. after it has read
+                    // these results.
                     ++n_t2;
-                    int* prod = reinterpret_cast<int*>(dreg);
+                    using CH = Chains<WW, WH>;
+                    int* buf = reinterpret_cast<int*>(dreg);
+                    if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }  // pads survive until the next level
 #pragma unroll
                     for (int k = 0; k < C::UPT; ++k)
                         if (unit_ok(k)) {
+                            const int y = unit_y(k), x0 = unit_x0(k);
+                            if (x0 >= C::NV) {
+                                float* tf = reinterpret_cast<float*>(buf) + 8 * CH::SLEN + y * CH::TL + (x0 - C::NV);
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                if (unit_x0(k) + jj < WW) {
-                                    const int slot = Chains<WW, WH>::slot_b(unit_y(k), unit_x0(k) + jj);
+                                for (int jj = 0; jj < 4; ++jj)
+                                    if (x0 + jj < WW) {
+                                        const int d = dd[k].get(jj);
+                                        tf[jj] = (float)(d * pxs[k][jj].gx());
+                                        tf[CH::TLEN + jj] = (float)(d * pxs[k][jj].gy());
+                                    }
+                            } else {
+                                int* si = buf + (y * CH::NS + (x0 >> 3)) * 2 + ((x0 >> 2) & 1);
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
                                     const int d = dd[k].get(jj);
-                                    prod[slot] = d * pxs[k][jj].gx();
-                                    prod[5 * Chains<WW, WH>::BLEN + slot] = d * pxs[k][jj].gy();
+                                    si[jj * CH::SLEN] = d * pxs[k][jj].gx();
+                                    si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
                                 }
+                            }
                         }
-                    if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(prod, tid); pads_zeroed = true; }  // pads survive until the next level
                     point_sync<WPP>(bar);
-                    replay_b<WW, WH>(prod, lane, b1, b2);  // every warp of the point computes the same values
-                    point_sync<WPP>(bar);  // scratch is rewritten by the next replay only after everyone is here
+                    replay_b<WW, WH, WPP>(buf, wip, lane);
+                    point_sync<WPP>(bar);
+                    const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
+                    const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
+                    const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
+                    b1 = combine5(r1.x, r1.y, r1.z, r1.w, rt.x);
+                    b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
                 }
             }
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
@@ -797,11 +827,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         L.err[gid] = err;
         if (L.iters) {
             // debug flag 0x100: cycles / 64 in the low 20 bits, tier-1 and tier-2 counts above (profiling aid)
-            // debug flag 0x200: start time (globaltimer ns / 32, low 16 bits) | duration (ns / 32) << 16
-            unsigned gt_end = 0;
-            if (L.flags & 0x200) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(gt_end));
-            if (L.flags & 0x200) L.iters[gid] = (int)(((gt_start >> 5) & 0xffffu) | (min((gt_end - gt_start) >> 5, 0xffffu) << 16));
-            else L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
+            L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
         }
     }
 }
