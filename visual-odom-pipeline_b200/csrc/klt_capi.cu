@@ -17,11 +17,14 @@ struct klt_ctx {
     int cc_major = 0, cc_minor = 0;
     char name[128] = {0};
     cudaStream_t stream = nullptr;  // for the *_host entry points
+    cudaStream_t stream2 = nullptr; // second copy stream of the *_host entry points
+    cudaEvent_t ev2 = nullptr;
     // device workspace of the *_host entry points (grown on demand, never shrunk)
     uint8_t* d_ws = nullptr;
     size_t d_ws_bytes = 0;
     // pinned staging for results (and for pageable inputs)
     uint8_t* h_ws = nullptr;
+    uint8_t* h_ws_dev = nullptr;   // device-side alias of h_ws
     size_t h_ws_bytes = 0;
 };
 
@@ -49,10 +52,13 @@ klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
 klt_status ensure_host_ws(klt_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->h_ws_bytes) return KLT_OK;
-    if (ctx->h_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_ws); ctx->h_ws = nullptr; ctx->h_ws_bytes = 0; }
+    if (ctx->h_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_ws); ctx->h_ws = nullptr; ctx->h_ws_dev = nullptr; ctx->h_ws_bytes = 0; }
     bytes = align_up(bytes + bytes / 4, 1 << 16);
-    cudaError_t e = cudaMallocHost(&ctx->h_ws, bytes);
+    cudaError_t e = cudaHostAlloc(&ctx->h_ws, bytes, cudaHostAllocMapped);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    void* alias = nullptr;
+    ctx->h_ws_dev = (cudaHostGetDevicePointer(&alias, ctx->h_ws, 0) == cudaSuccess) ? static_cast<uint8_t*>(alias) : nullptr;
+    cudaGetLastError();
     ctx->h_ws_bytes = bytes;
     return KLT_OK;
 }
@@ -133,9 +139,16 @@ klt_status klt_create(int device, klt_ctx** out)
     ctx->cc_minor = prop.minor;
     std::snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; return (klt_status)e; }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+        delete ctx;
+        return (klt_status)e;
+    }
     klt_status s = lk_init(device);
-    if (s != KLT_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return s; }
+    if (s != KLT_OK) { cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev2); delete ctx; return s; }
     *out = ctx;
     return KLT_OK;
 }
@@ -145,6 +158,8 @@ klt_status klt_destroy(klt_ctx* ctx)
     if (!ctx) return KLT_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->h_ws) cudaFreeHost(ctx->h_ws);
     delete ctx;
@@ -308,9 +323,16 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
         return std::chrono::duration<double, std::micro>(b - a).count();
     };
     const auto t0 = now();
+    // The two image copies go out on two streams so that both DMA engines work and the fixed latency of one copy
+    // hides behind the other (measured: zero-copy reads by the SMs are slower than the DMA engines for this size).
+    static const bool one_stream = getenv("KLT_ONE_COPY_STREAM") != nullptr;   // A/B runs
+    cudaStream_t st2 = one_stream ? st : ctx->stream2;
     if (linear) {
+        KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, next_img, raw_next, cudaMemcpyHostToDevice, st2));
+        if (st2 != st) KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
+        KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         KLT_CUDA(cudaMemcpyAsync(d + off_raw, prev_img, raw_prev, cudaMemcpyHostToDevice, st));
-        KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, next_img, raw_next, cudaMemcpyHostToDevice, st));
+        if (st2 != st) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
         if (prev_pitch == next_pitch) {
             s = repitch_launch(d + off_raw, prev_pitch, (long long)raw_slot, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 2, st);
         } else {
@@ -322,11 +344,11 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     } else {
         KLT_CUDA(cudaMemcpy2DAsync(d + off_img, ipitch, prev_img, (size_t)prev_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
         KLT_CUDA(cudaMemcpy2DAsync(d + off_img + ibytes, ipitch, next_img, (size_t)next_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+        KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     }
     float* d_next = reinterpret_cast<float*>(d + off_out);
     float* d_err = reinterpret_cast<float*>(d + off_out + (size_t)n * 8);
     uint8_t* d_status = d + off_out + (size_t)n * 12;
-    KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)
         KLT_CUDA(cudaMemcpyAsync(d_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     const auto t1 = now();
@@ -338,6 +360,15 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     LKLaunch L;
     make_view(&lay, d + off_img, d + off_pyr, 0, 1, L.prev);
     make_view(&lay, d + off_img, d + off_pyr, 1, 1, L.next);
+    // results: the kernel writes its 13 bytes per point straight into the context's page-locked staging buffer (mapped
+    // into the device address space), so no D2H copy is queued -- unless nextPts is also an input (initial flow)
+    static const bool no_direct = getenv("KLT_NO_DIRECT_OUT") != nullptr;   // A/B runs
+    const bool direct = !no_direct && !(params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW) && ctx->h_ws_dev != nullptr;
+    if (direct) {
+        d_next = reinterpret_cast<float*>(ctx->h_ws_dev);
+        d_err = reinterpret_cast<float*>(ctx->h_ws_dev + (size_t)n * 8);
+        d_status = ctx->h_ws_dev + (size_t)n * 12;
+    }
     L.prev_pts = reinterpret_cast<const float*>(d + off_pts);
     L.next_pts = d_next; L.status = d_status; L.err = d_err; L.iters = nullptr;
     L.n_per_pair = n; L.batch = 1;
@@ -350,7 +381,7 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     const auto t2 = now();
     if (trace) { cudaStreamSynchronize(st); }
     const auto t2s = now();
-    KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d + off_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (!direct) KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d + off_out, out_bytes, cudaMemcpyDeviceToHost, st));
     KLT_CUDA(cudaStreamSynchronize(st));
     const auto t3 = now();
     if (trace)
