@@ -131,6 +131,24 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx,
                         const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n,
                         int max_level, const klt_lk_params* params, int* top_level_out);
 
+/* ---- the reference's tracking step, fused ------------------------------ */
+/* Bidirectional-error / bounds filter, device pointers: reference src/extractor/extractor.py:46-47,53 (extend_tracks)
+ * and :67-68,75 (extend_landmarks):  bidir = max(|p0 - p0r|) over x, y;  keep = bidir < max_bidir_error and
+ * 0 <= p1.x <= w and 0 <= p1.y <= h (inclusive, as in the reference; NaN fails).  d_bidir_err may be NULL. */
+klt_status klt_track_filter(klt_ctx* ctx, const float* d_p0, const float* d_p1, const float* d_p0r, int64_t n,
+                            float max_bidir_error, int w, int h, uint8_t* d_keep, float* d_bidir_err, void* stream);
+
+/* One call for what extend_tracks / extend_landmarks do with cv2 (extractor.py:43-53, 64-75): p1 = LK(im0, im1, p0),
+ * p0r = LK(im0, im1, p1) (the reference's second call runs in the same direction, started from the forward result),
+ * then the filter above.  HOST buffers, synchronous.  One upload and ONE pyramid build per image instead of the four
+ * OpenCV builds two cv2 calls make.  next_pts / status / err are those of the first call (bit-identical to cv2's). */
+klt_status klt_track_bidirectional_host(klt_ctx* ctx,
+                        const uint8_t* prev_img, int64_t prev_pitch,
+                        const uint8_t* next_img, int64_t next_pitch, int w, int h,
+                        const float* prev_pts, int n, int max_level, const klt_lk_params* params,
+                        float max_bidir_error, float* next_pts, uint8_t* status, float* err,
+                        uint8_t* keep, float* bidir_err);
+
 /* cv2.buildOpticalFlowPyramid(img, winSize, maxLevel) without derivatives / borders: writes level
  * l (l = 0..top) tightly packed (pitch = level width) at out + level_offsets[l].  Pass out = NULL
  * to query `top` and the offsets / total size only. */

@@ -209,6 +209,52 @@ def test_reference_call_pattern_extend_tracks(klt, cv2):
     assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
 
 
+@pytest.mark.parametrize("max_err", [np.inf, 30, 28.5])
+def test_fused_tracking_step_equals_reference_pattern(klt, cv2, max_err):
+    """klt.trackBidirectional = the cv2 sequence of reference src/extractor/extractor.py:43-53 / :64-75 in one call:
+    p1 bit-exact, bidirectional distance bit-exact, survivor mask identical (hard motion + out-of-frame points)."""
+    lk = dict(winSize=(31, 31), maxLevel=3, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.03))
+    im0, im1 = S.frame_pair(240, 320, seed=5, motion=S.HARD)
+    p0 = S.uniform_points(700, 240, 320, seed=9, margin=25)          # some points start outside the frame
+    p0[3, 0, 0] = np.nan
+    p1, st, er = cv2.calcOpticalFlowPyrLK(im0, im1, p0, None, **lk)
+    p0r, _, _ = cv2.calcOpticalFlowPyrLK(im0, im1, p1, None, **lk)
+    with np.errstate(invalid="ignore"):
+        d = abs(p0 - p0r).reshape(-1, 2).max(-1)
+        good = d < max_err
+    x, y = p1.reshape(-1, 2).T
+    want = good & (0 <= x) & (x <= im1.shape[1]) & (0 <= y) & (y <= im1.shape[0])
+    q1, keep, bd, st2, er2 = klt.trackBidirectional(im0, im1, p0, max_bidir_error=max_err, **lk)
+    assert q1.shape == p0.shape and keep.dtype == np.bool_ and keep.shape == (700,)
+    fin = np.isfinite(p1).all(-1).ravel()
+    assert np.array_equal(q1.reshape(-1, 2)[fin].view(np.uint32), p1.reshape(-1, 2)[fin].view(np.uint32))
+    assert np.array_equal(st2, st)
+    m = st.ravel() == 1
+    assert np.array_equal(er2.ravel()[m].view(np.uint32), er.ravel()[m].view(np.uint32))
+    both = np.isfinite(d) & np.isfinite(bd)
+    assert np.array_equal(np.isfinite(d), np.isfinite(bd))
+    assert np.array_equal(bd[both].view(np.uint32), d[both].astype(np.float32).view(np.uint32))
+    assert np.array_equal(keep, want), "survivors differ at %s" % np.nonzero(keep != want)[0][:10]
+    assert want.sum() > 0 or max_err != np.inf
+    assert klt.trackBidirectional(im0, im1, np.empty((0, 1, 2), np.float32)) == (None,) * 5
+
+
+def test_device_track_filtered_equals_host_fused_step(klt, torch_cuda):
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    lk = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    pairs = [S.frame_pair(120, 160, seed=30 + i, motion=S.HARD if i % 2 else S.BENIGN) for i in range(3)]
+    pts = np.stack([S.uniform_points(150, 120, 160, seed=40 + i, margin=15).reshape(-1, 2) for i in range(3)])
+    trk = T.KLTTracker(**lk).reset(torch.from_numpy(np.stack([a for a, _ in pairs])).cuda())
+    p1, keep, bd, st, er = trk.track_filtered(torch.from_numpy(np.stack([b for _, b in pairs])).cuda(), torch.from_numpy(pts).cuda(), max_bidir_error=5.0)
+    for i, (a, b) in enumerate(pairs):
+        h1, hk, hb, hs, he = klt.trackBidirectional(a, b, pts[i], max_bidir_error=5.0, **lk)
+        assert np.array_equal(p1[i].cpu().numpy().view(np.uint32), h1.view(np.uint32))
+        assert np.array_equal(keep[i].cpu().numpy(), hk)
+        assert np.array_equal(bd[i].cpu().numpy().view(np.uint32), hb.view(np.uint32))
+        assert np.array_equal(st[i].cpu().numpy(), hs.ravel())
+
+
 # ---------------------------------------------------------------- device / batch API -------------
 def test_batched_device_api_equals_per_pair_host_calls(klt, oracle, torch_cuda):
     torch = torch_cuda

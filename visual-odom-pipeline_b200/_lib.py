@@ -50,6 +50,9 @@ SYMBOLS = {
                                 _c.POINTER(klt_lk_params), _P]),
     "klt_calc_optical_flow_pyr_lk_host": (_c.c_int, [_P, _P, _c.c_int64, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P,
                                                      _c.c_int, _c.c_int, _c.POINTER(klt_lk_params), _c.POINTER(_c.c_int)]),
+    "klt_track_filter": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_float, _c.c_int, _c.c_int, _P, _P, _P]),
+    "klt_track_bidirectional_host": (_c.c_int, [_P, _P, _c.c_int64, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int,
+                                                _c.POINTER(klt_lk_params), _c.c_float, _P, _P, _P, _P, _P]),
     "klt_build_optical_flow_pyramid_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                                        _P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int)]),
 }

@@ -279,10 +279,17 @@ klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* 
     return lk_launch(L, ctx->sm_count, (cudaStream_t)stream);
 }
 
-klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
-                                             const uint8_t* next_img, int64_t next_pitch, int w, int h,
-                                             const float* prev_pts, float* next_pts, uint8_t* status, float* err,
-                                             int n, int max_level, const klt_lk_params* params, int* top_level_out)
+}  // extern "C"
+
+namespace {
+
+// Shared worker of the host-pointer entry points: upload the pair, build both pyramids (one launch per level for the
+// two images), track.  bidir: run the reference's second call (same direction, started from the forward result) and the
+// bidirectional-error / bounds filter on the device as well -- one upload and one pyramid build for the whole step.
+klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch, const uint8_t* next_img, int64_t next_pitch,
+                      int w, int h, const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n,
+                      int max_level, const klt_lk_params* params, int* top_level_out, bool bidir, float max_bidir_error,
+                      uint8_t* keep, float* bidir_err)
 {
     if (!ctx || !params || !prev_img || !next_img || w <= 0 || h <= 0 || n < 0 || max_level < 0) return KLT_ERR_INVALID_ARG;
     if (prev_pitch < w || next_pitch < w) return KLT_ERR_INVALID_ARG;
@@ -302,11 +309,12 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     const size_t off_pyr = off_img + 2 * ibytes;
     const size_t off_pts = off_pyr + align_up((size_t)lay.bytes, 256);
     const size_t pts_bytes = align_up((size_t)n * 8, 256);
-    const size_t off_out = off_pts + pts_bytes;                 // nextPts | err | status, one D2H copy
-    const size_t out_bytes = (size_t)n * 8 + (size_t)n * 4 + (size_t)n;
+    const size_t off_out = off_pts + pts_bytes;                 // nextPts | err | [bidir err] | status | [keep], one D2H copy
+    const size_t out_bytes = (size_t)n * 8 + (size_t)n * 4 + (bidir ? (size_t)n * 4 : 0) + (size_t)n + (bidir ? (size_t)n : 0);
+    const size_t off_p0r = off_out + align_up(out_bytes, 256);  // second-call result (bidir only)
     // raw landing zone: each image arrives as ONE contiguous DMA in the caller's own row pitch and is re-pitched on
     // the device (a pitched 2-D copy of e.g. 1241-byte rows reaches a fraction of PCIe bandwidth)
-    const size_t off_raw = off_out + align_up(out_bytes, 256);
+    const size_t off_raw = off_p0r + (bidir ? pts_bytes : 0);
     const size_t raw_prev = (size_t)(h - 1) * (size_t)prev_pitch + (size_t)w;
     const size_t raw_next = (size_t)(h - 1) * (size_t)next_pitch + (size_t)w;
     const bool linear = raw_prev <= 2 * (size_t)w * h && raw_next <= 2 * (size_t)w * h;
@@ -348,7 +356,10 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     }
     float* d_next = reinterpret_cast<float*>(d + off_out);
     float* d_err = reinterpret_cast<float*>(d + off_out + (size_t)n * 8);
-    uint8_t* d_status = d + off_out + (size_t)n * 12;
+    float* d_bidir = reinterpret_cast<float*>(d + off_out + (size_t)n * 12);
+    const size_t o_status = (size_t)n * (bidir ? 16 : 12);
+    uint8_t* d_status = d + off_out + o_status;
+    uint8_t* d_keep = d_status + n;
     if (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)
         KLT_CUDA(cudaMemcpyAsync(d_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     const auto t1 = now();
@@ -363,7 +374,7 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     // results: the kernel writes its 13 bytes per point straight into the context's page-locked staging buffer (mapped
     // into the device address space), so no D2H copy is queued -- unless nextPts is also an input (initial flow)
     static const bool no_direct = getenv("KLT_NO_DIRECT_OUT") != nullptr;   // A/B runs
-    const bool direct = !no_direct && !(params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW) && ctx->h_ws_dev != nullptr;
+    const bool direct = !no_direct && !bidir && !(params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW) && ctx->h_ws_dev != nullptr;
     if (direct) {
         d_next = reinterpret_cast<float*>(ctx->h_ws_dev);
         d_err = reinterpret_cast<float*>(ctx->h_ws_dev + (size_t)n * 8);
@@ -378,6 +389,19 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
     L.min_eig_thr = (float)params->min_eig_threshold;
     s = lk_launch(L, ctx->sm_count, st);
     if (s != KLT_OK) return s;
+    if (bidir) {
+        // second call of the reference (extractor.py:45,66): same image pair, prevPts = the forward result.  The
+        // reference discards its status / err, so they land in the keep / bidir slots that the filter overwrites next.
+        LKLaunch L2 = L;
+        L2.prev_pts = d_next;
+        L2.next_pts = reinterpret_cast<float*>(d + off_p0r);
+        L2.status = d_keep;                       // overwritten by the filter below
+        L2.err = d_bidir;                         // idem
+        s = lk_launch(L2, ctx->sm_count, st);
+        if (s != KLT_OK) return s;
+        s = track_filter_launch(L.prev_pts, d_next, L2.next_pts, n, max_bidir_error, w, h, d_keep, d_bidir, st);
+        if (s != KLT_OK) return s;
+    }
     const auto t2 = now();
     if (trace) { cudaStreamSynchronize(st); }
     const auto t2s = now();
@@ -389,8 +413,44 @@ klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_i
                      us(t0, t1), us(t1, t1s), us(t1s, t2), us(t2, t2s), us(t2s, t3));
     std::memcpy(next_pts, ctx->h_ws, (size_t)n * 8);
     std::memcpy(err, ctx->h_ws + (size_t)n * 8, (size_t)n * 4);
-    std::memcpy(status, ctx->h_ws + (size_t)n * 12, (size_t)n);
+    std::memcpy(status, ctx->h_ws + o_status, (size_t)n);
+    if (bidir) {
+        std::memcpy(bidir_err, ctx->h_ws + (size_t)n * 12, (size_t)n * 4);
+        std::memcpy(keep, ctx->h_ws + o_status + n, (size_t)n);
+    }
     return KLT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
+                                             const uint8_t* next_img, int64_t next_pitch, int w, int h,
+                                             const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                                             int n, int max_level, const klt_lk_params* params, int* top_level_out)
+{
+    return track_host(ctx, prev_img, prev_pitch, next_img, next_pitch, w, h, prev_pts, next_pts, status, err, n, max_level,
+                      params, top_level_out, false, 0.f, nullptr, nullptr);
+}
+
+klt_status klt_track_bidirectional_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
+                                        const uint8_t* next_img, int64_t next_pitch, int w, int h,
+                                        const float* prev_pts, int n, int max_level, const klt_lk_params* params,
+                                        float max_bidir_error, float* next_pts, uint8_t* status, float* err,
+                                        uint8_t* keep, float* bidir_err)
+{
+    if (n > 0 && (!keep || !bidir_err)) return KLT_ERR_INVALID_ARG;
+    if (params && (params->flags & KLT_OPTFLOW_USE_INITIAL_FLOW)) return KLT_ERR_INVALID_ARG;   // the reference passes nextPts = None
+    return track_host(ctx, prev_img, prev_pitch, next_img, next_pitch, w, h, prev_pts, next_pts, status, err, n, max_level,
+                      params, nullptr, true, max_bidir_error, keep, bidir_err);
+}
+
+klt_status klt_track_filter(klt_ctx* ctx, const float* d_p0, const float* d_p1, const float* d_p0r, int64_t n,
+                            float max_bidir_error, int w, int h, uint8_t* d_keep, float* d_bidir_err, void* stream)
+{
+    if (!ctx) return KLT_ERR_INVALID_ARG;
+    return track_filter_launch(d_p0, d_p1, d_p0r, (long long)n, max_bidir_error, w, h, d_keep, d_bidir_err, (cudaStream_t)stream);
 }
 
 klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,

@@ -141,6 +141,48 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, status=None, e
     return out.reshape(shape), st, er
 
 
+def trackBidirectional(prevImg, nextImg, prevPts, max_bidir_error=30, winSize=(31, 31), maxLevel=3,
+                       criteria=(TERM_COUNT | TERM_EPS, 30, 0.03), minEigThreshold=1e-4, device=0):
+    """The KLT part of the reference's ``extend_tracks`` / ``extend_landmarks`` in one call
+    (src/extractor/extractor.py:43-53 and :64-75; defaults = its ``_lk_params``, :16-19):
+
+        p1, st, err = cv2.calcOpticalFlowPyrLK(im0, im1, p0, None, **lk)
+        p0r, _, _   = cv2.calcOpticalFlowPyrLK(im0, im1, p1, None, **lk)     # same direction, as in the reference
+        d    = abs(p0 - p0r).reshape(-1, 2).max(-1)
+        keep = (d < max_bidir_error) & (0 <= x <= W) & (0 <= y <= H)          # (x, y) = p1
+
+    -> (p1 like prevPts, keep (N,) bool, d (N,) float32, status (N,1) uint8, err (N,1) float32).
+    One upload and one pyramid build per image (cv2 builds four pyramids for the two calls), both LK passes and the
+    filter on the device; p1 / status / err are bit-identical to cv2's first call.  N == 0 -> (None,) * 5.
+    """
+    win_w, win_h, maxLevel = _check_win_level(winSize, maxLevel)
+    prev = _host_image(prevImg, "prevImg")
+    nxt = _host_image(nextImg, "nextImg")
+    if prev.shape != nxt.shape:
+        _fail("prevPyr[level * lvlStep1].size() == nextPyr[level * lvlStep2].size() in function 'calc'")
+    pts, shape = _host_points(prevPts, "prevPts")
+    n = pts.shape[0]
+    if n == 0:
+        return None, None, None, None, None
+    params = make_params((win_w, win_h), criteria, 0, minEigThreshold)
+    out = np.empty((n, 2), np.float32)
+    st = np.empty((n, 1), np.uint8)
+    er = np.empty((n, 1), np.float32)
+    keep = np.empty(n, np.uint8)
+    bd = np.empty(n, np.float32)
+    h, w = prev.shape
+    ctx = _lib.default_context(device)
+    L = _lib.load()
+    with ctx.lock:
+        rc = L.klt_track_bidirectional_host(
+            ctx.handle, prev.ctypes.data, prev.strides[0], nxt.ctypes.data, nxt.strides[0], w, h, pts.ctypes.data, n,
+            maxLevel, ctypes.byref(params), float(max_bidir_error),
+            out.ctypes.data, st.ctypes.data, er.ctypes.data, keep.ctypes.data, bd.ctypes.data)
+    if rc != KLT_OK:
+        _raise_status(rc, "trackBidirectional")
+    return out.reshape(shape), keep.view(np.bool_), bd, st, er
+
+
 def buildOpticalFlowPyramid(img, winSize, maxLevel, pyramid=None, withDerivatives=False, pyrBorder=None,
                             derivBorder=None, tryReuseInputImage=True, device=0):
     """cv2.buildOpticalFlowPyramid(img, winSize, maxLevel, withDerivatives=False) -> (retval, pyramid).

@@ -163,6 +163,23 @@ def calc_optical_flow_pyr_lk_device(prevImg, nextImg, prevPts, nextPts=None, win
     return out, st, er
 
 
+def track_filter(p0, p1, p0r, max_bidir_error, w, h, ctx=None):
+    """Bidirectional-error / bounds filter of reference src/extractor/extractor.py:46-47,53 on CUDA tensors.
+    p0, p1, p0r: (..., 2) float32 -> keep (...) bool, bidir (...) float32."""
+    torch = _torch()
+    a, b, c = p0.contiguous(), p1.contiguous(), p0r.contiguous()
+    n = a.numel() // 2
+    keep = torch.empty(a.shape[:-1], dtype=torch.uint8, device=a.device)
+    bidir = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+    if n:
+        ctx = ctx or _lib.default_context(a.device.index or 0)
+        rc = _lib.load().klt_track_filter(ctx.handle, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, float(max_bidir_error), int(w), int(h),
+                                          keep.data_ptr(), bidir.data_ptr(), _stream_ptr(a))
+        if rc != KLT_OK:
+            _raise_status(rc, "klt_track_filter")
+    return keep.bool(), bidir
+
+
 class KLTTracker:
     """Frame-to-frame tracker that keeps the last frame's pyramid on the device.
 
@@ -195,3 +212,13 @@ class KLTTracker:
             out = out + (back[0],)
         self.prev = nxt
         return out
+
+    def track_filtered(self, images, prevPts, max_bidir_error=30):
+        """The reference's whole KLT step for a batch of sequences (extractor.py:43-53): forward pass, the second pass
+        started from the forward result, bidirectional-error and inclusive-bounds filter -- all on the device, the
+        new frame's pyramid built once and kept as the next `prev`.
+        -> p1 (B, N, 2), keep (B, N) bool, bidir (B, N) float32, status (B, N) uint8, err (B, N) float32"""
+        p1, st, er, p0r = self.track(images, prevPts, bidirectional=True)
+        H, W = self.prev.images.shape[1], self.prev.images.shape[2]
+        keep, bidir = track_filter(prevPts, p1, p0r, max_bidir_error, W, H, ctx=self.prev.ctx)
+        return p1, keep, bidir, st, er
