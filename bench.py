@@ -125,6 +125,26 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_counters(report, pick_largest_grid=False):
+    """Counters of the committed ncu capture of a kernel (profiles/r01/counters.json, written by
+    scripts/summarize_profiles.py from `ncu --set full` runs of scripts/prof_target.py): DRAM traffic per launch and the
+    utilisation figures the north star asks for.  Profiler figures, labelled as such -- never timings of this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "counters.json")) as f:
+            rows = json.load(f).get(report) or []
+        if not rows:
+            return None
+        def grid_size(r):
+            try:
+                return int(str(r.get("grid", "0")).strip("() ").split(",")[0])
+            except ValueError:
+                return 0
+        row = max(rows, key=grid_size) if pick_largest_grid else rows[-1]
+        return row
+    except Exception:
+        return None
+
+
 def time_cv2(wl, pool, reps, warm, threads=None):
     import cv2
     if threads is not None:
@@ -270,6 +290,38 @@ def main():
     dev_ms = sharding.max_over_ranks(ev0.elapsed_time(ev1))
     value = world * n * args.steps / (dev_ms * 1e-3)
 
+    # ---- the same steps pipelined over 4 streams: independent pairs overlap, the idle tail of one pair's LK launch is
+    # filled by the next pair (throughput of a job of independent pairs; per-pair latency is the number above) -------
+    n_str = 4
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
+    sptrs = [ctypes.c_void_p(st_.cuda_stream) for st_ in side]
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step_on(i, sp):
+        rc = L.klt_pyr_build(h_ctx, img0, layB_ref, pyr0, 2 * i, 2, sp)
+        assert rc == 0, _lib.status_string(rc)
+        rc = L.klt_lk_track(h_ctx, img0, pyr0, img0, pyr0, layB_ref, 2 * i, 2 * i + 1, 2, 1, pts0 + i * n * 8, q0 + i * n * 8,
+                            s0 + i * n, e0 + i * n * 4, None, n, params_ref, sp)
+        assert rc == 0, _lib.status_string(rc)
+
+    for rep in range(2):      # first pass = warm-up
+        torch.cuda.synchronize()
+        sharding.barrier()
+        pe0.record(stream)
+        for st_ in side:
+            st_.wait_event(pe0)
+        for s_ in range(args.steps):
+            step_on((args.warmup + s_) % P, sptrs[s_ % n_str])
+        for st_ in side:
+            ev = torch.cuda.Event()
+            ev.record(st_)
+            stream.wait_event(ev)
+        pe1.record(stream)
+        torch.cuda.synchronize()
+    pipe_ms = sharding.max_over_ranks(pe0.elapsed_time(pe1))
+    pipelined = {"streams": n_str, "keypoints_per_sec": world * n * args.steps / (pipe_ms * 1e-3), "pairs_per_sec": world * args.steps / (pipe_ms * 1e-3),
+                 "ms_per_step": pipe_ms / args.steps, "note": "same steps, independent pairs issued round-robin on 4 streams"}
+
     # ---- per-kernel durations over the same steps (events on the launching stream) ---------------------------
     ksteps = min(args.steps, 200)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(ksteps)]
@@ -317,8 +369,14 @@ def main():
         lk_bytes_pt = levels * (win[0] + 3) * (win[1] + 3) + it_mean * (win[0] + 1) * (win[1] + 1)
         lk_achieved = lk_bytes_pt * n / (lk_ms * 1e-3) / 1e9
         mac_pt = win[0] * win[1] * (15 * levels + 7 * it_mean + 6)
-        roofline = {"kernel": "lk_kernel (fused Scharr + pyramidal LK, all levels, 1 launch)", "bound": "hbm",
-                    "achieved": lk_achieved, "peak": peak, "unit": "GB/s", "frac": lk_achieved / peak, "traffic": None,
+        c_lk = ncu_counters("prof_lk") if wl_name == "kitti" else None
+        roofline = {"kernel": "lk_fast_kernel (fused Scharr + pyramidal LK, all levels, 1 launch)", "bound": "hbm",
+                    "achieved": lk_achieved, "peak": peak, "unit": "GB/s", "frac": lk_achieved / peak,
+                    "traffic": (c_lk["dram_bytes_read"] + c_lk["dram_bytes_write"]) if c_lk else None,
+                    "ncu": ({"source": "profiles/r01/counters.json (ncu --set full of the same launch shape; profiler figures)",
+                             "issue_slots_active_pct": c_lk["issue_active_pct"], "shared_mem_wavefronts_pct_of_peak": c_lk["smem_wavefronts_pct_of_peak"],
+                             "sm_active_fraction_of_elapsed": (c_lk["sm_active_cycles_avg"] / c_lk["sm_elapsed_cycles_max"]) if c_lk.get("sm_elapsed_cycles_max") else None}
+                            if c_lk else None),
                     "peak_source": peak_src, "launch_ms": lk_ms, "algorithmic_bytes_per_launch": lk_bytes_pt * n,
                     "iters_per_point": it_mean, "int_mac_per_point": mac_pt, "gmac_per_s": mac_pt * n / (lk_ms * 1e-3) / 1e9,
                     "note": "working set is L2/L1-resident: this kernel is issue/latency-bound, not HBM-bound (see DESIGN.md, profiles/)"}
@@ -350,7 +408,10 @@ def main():
             ball += nb * (layB.level[l].w * layB.level[l].h + layB.level[l + 1].w * layB.level[l + 1].h)
         pyr_roof = {"kernel": "pyr_down_kernel level 0->1, batch of %d images (%.0f MB read, > L2)" % (nb, nb * w * h / 1e6),
                     "bound": "hbm", "achieved": b01 / (d01_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": b01 / (d01_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "launch_ms": d01_ms,
+                    "frac": b01 / (d01_ms * 1e-3) / 1e9 / peak,
+                    "traffic": ((lambda c: (c["dram_bytes_read"] + c["dram_bytes_write"]) if c else None)(ncu_counters("prof_pyr", True)) if (w, h) == (1241, 376) else None),
+                    "traffic_note": "ncu dram__bytes_read+write of the same launch (310 KITTI images), profiles/r01/counters.json; part of the output is still in L2 at kernel end",
+                    "peak_source": peak_src, "launch_ms": d01_ms,
                     "algorithmic_bytes_per_launch": b01,
                     "whole_pyramid": {"levels_built": int(layB.top), "ms": full_ms, "algorithmic_bytes": ball,
                                       "achieved": ball / (full_ms * 1e-3) / 1e9, "frac": ball / (full_ms * 1e-3) / 1e9 / peak}}
@@ -418,6 +479,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "pyramid_roofline": pyr_roof,
+            "pipelined": pipelined,
             "batched_lk": batched,
             "parity": parity,
             "cpu_baseline": cpu,

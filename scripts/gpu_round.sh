@@ -12,7 +12,7 @@ python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 tail -c 600 $OUT/bench.err
 python bench.py --workload kitti_ref_params --steps 200 > $OUT/bench_win31.json 2>> $OUT/bench.err
 # launch list of the same bench command (cold-cache, serialised: shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file $OUT/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 466 -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 40 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 # full captures: batched pyramid kernel (level 0->1 of 310 KITTI images) and the single-pair LK kernel
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pyr_down -c 3 -o $OUT/prof_pyr -f \

@@ -48,7 +48,7 @@ if os.path.exists(launches):
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(dst, "launches_summary.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 40 --warmup 3 --no-cpu-baseline`\n")
-        f.write("(-s 60 -c 400: setup copies skipped; per-launch times are cold-cache and serialised -> shares only)\n")
+        f.write("(-s 466 -c 400: the pool-setup copies are skipped; per-launch times are cold-cache and serialised -> shares only)\n")
         f.write("%d launches captured, %.1f us total\n\n" % (len(rows), tot))
         f.write("%-60s %8s %12s %10s %7s  %s\n" % ("kernel", "launches", "total us", "avg us", "share", "grid x block (first)"))
         for k, (n, us, g, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -67,4 +67,53 @@ for rep in sorted(os.listdir(src)):
         with open(os.path.join(dst, rep.replace(".ncu-rep", "_hot_lines.txt")), "w") as f:
             f.write("per-source-line share of executed warp-instructions and of stall samples (top 25 lines per kernel)\n")
             f.write(out)
+# machine-readable counters of the captured kernels (bench.py copies `traffic` and the issue / shared-memory utilisation
+# from here into its JSON line, labelled as ncu figures)
+import json
+
+
+def raw_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        return []
+    hdr, units = rows[0], rows[1]
+    return [{h.strip(): (v, u) for h, u, v in zip(hdr, units, r)} for r in rows[2:]]
+
+
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,      # to bytes
+         "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}   # to us
+
+
+def num(d, key):
+    if key not in d:
+        return None
+    v, u = d[key]
+    try:
+        return float(v.replace(",", "")) * SCALE.get(u.strip(), 1.0)
+    except ValueError:
+        return None
+
+
+counters = {}
+for rep in sorted(os.listdir(src)):
+    if not rep.endswith(".ncu-rep"):
+        continue
+    for d in raw_rows(os.path.join(src, rep)):
+        name = short(d.get("Kernel Name", ("", ""))[0])
+        rd, wr = num(d, "dram__bytes_read.sum"), num(d, "dram__bytes_write.sum")
+        entry = {
+            "report": rep, "kernel": name, "grid": d.get("launch__grid_size", ("", ""))[0].strip(),
+            "duration_us_under_ncu": num(d, "gpu__time_duration.sum"),
+            "dram_bytes_read": rd, "dram_bytes_write": wr,
+            "issue_active_pct": num(d, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "smem_wavefronts_pct_of_peak": num(d, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+            "warps_active_pct": num(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "dram_throughput_pct": num(d, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "registers_per_thread": num(d, "launch__registers_per_thread"),
+            "sm_active_cycles_avg": num(d, "smsp__cycles_active.avg"), "sm_elapsed_cycles_max": num(d, "sm__cycles_elapsed.max"),
+        }
+        counters.setdefault(rep.replace(".ncu-rep", ""), []).append(entry)
+with open(os.path.join(dst, "counters.json"), "w") as f:
+    json.dump(counters, f, indent=1)
 print("wrote", sorted(os.listdir(dst)))
