@@ -2,6 +2,7 @@
 // and the host-pointer entry points that stand in for cv2.calcOpticalFlowPyrLK /
 // cv2.buildOpticalFlowPyramid as called from reference src/extractor/extractor.py:44,45,65,66.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +98,17 @@ void normalise_criteria(const klt_lk_params* p, int& max_count, double& eps2)
     if ((p->crit_type & KLT_TERM_EPS) == 0) eps = 0.01;
     else eps = p->crit_eps < 0. ? 0. : (p->crit_eps > 10. ? 10. : p->crit_eps);
     eps2 = eps * eps;
+}
+
+void set_eps_brackets(LKLaunch& L)
+{
+    if (L.eps2 >= 1e-30 && L.eps2 <= 1e30) {
+        L.eps2_lo = std::nextafterf((float)(L.eps2 * (1.0 - 1.0 / 1048576.0)), -1.f);
+        L.eps2_hi = std::nextafterf((float)(L.eps2 * (1.0 + 1.0 / 1048576.0)), 3.0e38f);
+    } else {
+        L.eps2_lo = -1.f;
+        L.eps2_hi = __builtin_inff();
+    }
 }
 
 }  // namespace
@@ -274,6 +286,7 @@ klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* 
     L.batch = n_pairs;
     L.win_w = params->win_w; L.win_h = params->win_h;
     normalise_criteria(params, L.max_count, L.eps2);
+    set_eps_brackets(L);
     L.flags = params->flags;
     L.min_eig_thr = (float)params->min_eig_threshold;
     return lk_launch(L, ctx->sm_count, (cudaStream_t)stream);
@@ -385,6 +398,7 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     L.n_per_pair = n; L.batch = 1;
     L.win_w = params->win_w; L.win_h = params->win_h;
     normalise_criteria(params, L.max_count, L.eps2);
+    set_eps_brackets(L);
     L.flags = params->flags;
     L.min_eig_thr = (float)params->min_eig_threshold;
     s = lk_launch(L, ctx->sm_count, st);

@@ -61,6 +61,10 @@ struct LKLaunch {
     int win_w, win_h;
     int max_count;
     double eps2;
+    // float brackets of eps2 for the termination test: dx*dx + dy*dy evaluated in float32 is within 2^-22 (relative) of
+    // the double value OpenCV compares, so  s <= eps2_lo  decides "<= eps2" and  s >= eps2_hi  decides "> eps2"; only
+    // values in between (practically never) take the double-precision path.  lo < 0 / hi = inf disable the shortcut.
+    float eps2_lo, eps2_hi;
     int flags;
     float min_eig_thr;
 };

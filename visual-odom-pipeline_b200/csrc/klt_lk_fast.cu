@@ -770,8 +770,15 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             outp = make_float2(__fadd_rn(nx, hwx), __fadd_rn(ny, hwy));
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2) break;
-            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+            {   // termination tests of A.4 6f / 6g without double-precision instructions on the common path
+                const float s2f = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                bool small = s2f <= L.eps2_lo;
+                if (!small && !(s2f >= L.eps2_hi))
+                    small = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2;
+                if (small) break;
+            }
+            // (double)f < 0.01  <=>  f <= 0.01f: the float nearest to 0.01 lies below it, the next float above it
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                 outp.x = __fsub_rn(outp.x, __fmul_rn(dx, 0.5f));
                 outp.y = __fsub_rn(outp.y, __fmul_rn(dy, 0.5f));
                 break;
