@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KLT_B200_VERSION 100 /* 0.1.0 */
+#define KLT_B200_VERSION 110 /* 0.1.1: + corner detection */
 
 #define KLT_MAX_LEVELS 16   /* pyramid levels incl. level 0 (cv2 stops when a level <= winSize) */
 #define KLT_MAX_WIN_AREA 4096 /* win_w * win_h supported by the LK kernel (cv2 default 21x21) */
@@ -155,6 +155,50 @@ klt_status klt_track_bidirectional_host(klt_ctx* ctx,
 klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
                         int win_w, int win_h, int max_level, uint8_t* out, int64_t* level_offsets /*[KLT_MAX_LEVELS+1]*/,
                         int* top_out);
+
+/* ---- Shi-Tomasi corner detection -------------------------------------------------------
+ * Replaces cv2.goodFeaturesToTrack(img, mask=mask, maxCorners=1000, qualityLevel=0.03, minDistance, blockSize=31)
+ * as called at reference src/extractor/extractor.py:110-111 (parameters :21-24; once per frame from
+ * src/pipeline/pipeline.py:159-163) and the cv2.cornerMinEigenVal it runs inside (gradient size 3, no Harris).
+ * Arithmetic: oracle/gftt_oracle.c G.1-G.8, bit-exact with the cv2 wheel of the image. */
+
+/* Bytes of device scratch klt_corner_min_eigen_val needs for a batch of w x h images. */
+int64_t klt_corner_ws_bytes(int w, int h, int batch);
+
+/* cv2.cornerMinEigenVal(src, blockSize, ksize=3), device pointers, batched, asynchronous.  d_img: u8, any pitch;
+ * d_eig: float32, eig_pitch / eig_batch_stride in ELEMENTS.  d_max (optional): one uint32 per batch item, zeroed by
+ * the caller, receives the order-preserving encoding of the maximum eigenvalue over mask != 0 (d_mask optional =
+ * everywhere); it is the input of klt_corner_candidates.  d_ws: klt_corner_ws_bytes() bytes, 256-byte aligned. */
+klt_status klt_corner_min_eigen_val(klt_ctx* ctx, const uint8_t* d_img, int w, int h, int64_t pitch, int64_t batch_stride,
+                        int batch, int block_size, float* d_eig, int64_t eig_pitch, int64_t eig_batch_stride,
+                        const uint8_t* d_mask, int64_t mask_pitch, int64_t mask_batch_stride, uint32_t* d_max,
+                        void* d_ws, int64_t ws_bytes, void* stream);
+
+/* Threshold (max * quality_level), 3x3 dilation and local-maximum test of goodFeaturesToTrack fused: appends one
+ * 64-bit key per candidate, (order-preserving float encoding << 32) | (y * w + x), in arbitrary order, to d_keys
+ * (capacity keys per batch item, keys_batch_stride in ELEMENTS).  d_count: one uint32 per batch item, zeroed by the
+ * caller, receives the number of candidates (may exceed capacity: the excess is dropped). */
+klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_pitch, int64_t eig_batch_stride, int w, int h,
+                        int batch, const uint8_t* d_mask, int64_t mask_pitch, int64_t mask_batch_stride,
+                        const uint32_t* d_max, double quality_level, uint64_t* d_keys, int64_t keys_batch_stride,
+                        int capacity, uint32_t* d_count, void* stream);
+
+/* The sequential tail of goodFeaturesToTrack on the HOST: sorts the keys (strongest first, ties by descending
+ * y * w + x like OpenCV) in place and runs the greedy minimum-distance selection.  corners: capacity x (x, y) floats;
+ * *n_out = corners found (<= max_corners if max_corners > 0). */
+klt_status klt_select_corners_host(uint64_t* keys, int64_t n_keys, int w, int h, int max_corners, double min_distance,
+                        float* corners, int capacity, int* n_out);
+
+/* cv2.cornerMinEigenVal(img, blockSize, ksize=3) with HOST buffers, synchronous.  eig: h x w float32, packed. */
+klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h, int block_size,
+                        float* eig);
+
+/* cv2.goodFeaturesToTrack(img, maxCorners, qualityLevel, minDistance, mask, blockSize) with HOST buffers, synchronous.
+ * mask may be NULL.  corners: capacity x (x, y) float32, strongest first; *n_out = number found (cv2 returns None for
+ * 0).  KLT_ERR_INVALID_ARG where cv2 asserts (quality_level <= 0, min_distance < 0, max_corners < 0). */
+klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                        const uint8_t* mask, int64_t mask_pitch, int max_corners, double quality_level,
+                        double min_distance, int block_size, float* corners, int capacity, int* n_out);
 
 #ifdef __cplusplus
 }

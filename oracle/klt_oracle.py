@@ -21,8 +21,8 @@ USE_INITIAL_FLOW, GET_MIN_EIGENVALS = 4, 8
 
 def build(force=False):
     """Compile the oracle with gcc (seconds)."""
-    src = os.path.join(_HERE, "klt_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("klt_oracle.c", "gftt_oracle.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
     return _SO
 
@@ -44,6 +44,14 @@ def lib():
             c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int,
             c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_double, c.c_int, c.c_double, c.c_void_p]
         L.klt_oracle_calc_optical_flow_pyr_lk.restype = c.c_int
+        L.klt_oracle_corner_min_eigen_val.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int64, c.c_int, c.c_void_p]
+        L.klt_oracle_corner_min_eigen_val.restype = c.c_int
+        L.klt_oracle_select_corners.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int64, c.c_int, c.c_double,
+                                                c.c_double, c.c_void_p, c.c_int]
+        L.klt_oracle_select_corners.restype = c.c_int
+        L.klt_oracle_good_features_to_track.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int64, c.c_void_p, c.c_int64, c.c_int,
+                                                        c.c_double, c.c_double, c.c_int, c.c_void_p, c.c_int]
+        L.klt_oracle_good_features_to_track.restype = c.c_int
         _lib = L
     return _lib
 
@@ -122,3 +130,57 @@ def calc_optical_flow_pyr_lk(prev_img, next_img, prev_pts, next_pts=None, win_si
         raise ValueError("oracle: invalid arguments (rc=%d)" % rc)
     out = (q.reshape(shape), status, err)
     return out + (iters,) if return_iters else out
+
+
+def corner_min_eigen_val(img, block_size, ksize=3):
+    """cv2.cornerMinEigenVal(img, blockSize, ksize=3) -> float32 (h, w)   (oracle/gftt_oracle.c G.1-G.6)."""
+    if ksize != 3:
+        raise ValueError("oracle: only ksize 3")
+    img = _u8_image(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.float32)
+    rc = lib().klt_oracle_corner_min_eigen_val(img.ctypes.data, w, h, img.strides[0], int(block_size), out.ctypes.data)
+    if rc < 0:
+        raise ValueError("oracle: corner_min_eigen_val failed (%d)" % rc)
+    return out
+
+
+def _mask(mask, shape):
+    if mask is None:
+        return None, 0, 0
+    mask = np.asarray(mask)
+    if mask.dtype != np.uint8 or mask.shape != shape:
+        raise ValueError("oracle: mask must be uint8 of the image's shape")
+    if mask.strides[1] != 1:
+        mask = np.ascontiguousarray(mask)
+    return mask, mask.ctypes.data, mask.strides[0]
+
+
+def select_corners(eig, max_corners, quality_level, min_distance, mask=None):
+    """G.7 + G.8 on a given eigenvalue map -> float32 (n, 1, 2) or None."""
+    eig = np.ascontiguousarray(eig, np.float32)
+    h, w = eig.shape
+    mask, mp, ms = _mask(mask, (h, w))
+    cap = w * h
+    out = np.empty((cap, 2), np.float32)
+    n = lib().klt_oracle_select_corners(eig.ctypes.data, w, h, mp, ms, int(max_corners), float(quality_level),
+                                        float(min_distance), out.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("oracle: select_corners failed (%d)" % n)
+    return out[:n].reshape(-1, 1, 2).copy() if n else None
+
+
+def good_features_to_track(img, max_corners, quality_level, min_distance, mask=None, block_size=3):
+    """cv2.goodFeaturesToTrack(img, maxCorners, qualityLevel, minDistance, mask=mask, blockSize=...) as called at
+    reference src/extractor/extractor.py:110-111 -> float32 (n, 1, 2) or None."""
+    img = _u8_image(img)
+    h, w = img.shape
+    mask, mp, ms = _mask(mask, (h, w))
+    cap = w * h
+    out = np.empty((cap, 2), np.float32)
+    n = lib().klt_oracle_good_features_to_track(img.ctypes.data, w, h, img.strides[0], mp, ms, int(max_corners),
+                                                float(quality_level), float(min_distance), int(block_size),
+                                                out.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("oracle: good_features_to_track failed (%d)" % n)
+    return out[:n].reshape(-1, 1, 2).copy() if n else None

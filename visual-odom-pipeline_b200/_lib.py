@@ -55,6 +55,16 @@ SYMBOLS = {
                                                 _c.POINTER(klt_lk_params), _c.c_float, _P, _P, _P, _P, _P]),
     "klt_build_optical_flow_pyramid_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                                        _P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int)]),
+    "klt_corner_ws_bytes": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
+    "klt_corner_min_eigen_val": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int64,
+                                            _c.c_int64, _P, _c.c_int64, _c.c_int64, _P, _P, _c.c_int64, _P]),
+    "klt_corner_candidates": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int64, _c.c_int64,
+                                         _P, _c.c_double, _P, _c.c_int64, _c.c_int, _P, _P]),
+    "klt_select_corners_host": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _P, _c.c_int,
+                                           _c.POINTER(_c.c_int)]),
+    "klt_corner_min_eigen_val_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _P]),
+    "klt_good_features_to_track_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int64, _c.c_int, _c.c_double,
+                                                   _c.c_double, _c.c_int, _P, _c.c_int, _c.POINTER(_c.c_int)]),
 }
 
 _lib = None

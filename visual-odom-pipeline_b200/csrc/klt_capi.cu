@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
 #include <new>
+#include <vector>
 
 #include "klt_common.cuh"
 
@@ -505,6 +508,233 @@ klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img,
     }
     KLT_CUDA(cudaStreamSynchronize(st));
     return KLT_OK;
+}
+
+// ---- Shi-Tomasi corner detection (kernels in klt_corners.cu) -----------------------------------
+
+int64_t klt_corner_ws_bytes(int w, int h, int batch)
+{
+    if (w < 1 || h < 1 || batch < 1) return 0;
+    return (int64_t)corners_ws_bytes(w, h, batch);
+}
+
+klt_status klt_corner_min_eigen_val(klt_ctx* ctx, const uint8_t* d_img, int w, int h, int64_t pitch, int64_t batch_stride,
+                                    int batch, int block_size, float* d_eig, int64_t eig_pitch, int64_t eig_batch_stride,
+                                    const uint8_t* d_mask, int64_t mask_pitch, int64_t mask_batch_stride, uint32_t* d_max,
+                                    void* d_ws, int64_t ws_bytes, void* stream)
+{
+    if (!ctx || !d_img || !d_eig || !d_ws || pitch < w || eig_pitch < w) return KLT_ERR_INVALID_ARG;
+    if (w < 1 || h < 1 || batch < 1 || block_size < 1) return KLT_ERR_INVALID_ARG;
+    if (ws_bytes < (int64_t)corners_ws_bytes(w, h, batch) || ((uintptr_t)d_ws & 255)) return KLT_ERR_INVALID_ARG;
+    if (d_mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
+    return corner_min_eig_launch(d_img, pitch, batch_stride, w, h, batch, block_size, d_eig, eig_pitch, eig_batch_stride,
+                                 d_mask, mask_pitch, mask_batch_stride, d_max, d_ws, (cudaStream_t)stream);
+}
+
+klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_pitch, int64_t eig_batch_stride, int w, int h,
+                                 int batch, const uint8_t* d_mask, int64_t mask_pitch, int64_t mask_batch_stride,
+                                 const uint32_t* d_max, double quality_level, uint64_t* d_keys, int64_t keys_batch_stride,
+                                 int capacity, uint32_t* d_count, void* stream)
+{
+    if (!ctx || !d_eig || !d_max || !d_keys || !d_count || eig_pitch < w) return KLT_ERR_INVALID_ARG;
+    if (d_mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
+    return corner_candidates_launch(d_eig, eig_pitch, eig_batch_stride, w, h, batch, d_mask, mask_pitch, mask_batch_stride,
+                                    d_max, quality_level, reinterpret_cast<unsigned long long*>(d_keys), keys_batch_stride,
+                                    capacity, d_count, (cudaStream_t)stream);
+}
+
+klt_status klt_select_corners_host(uint64_t* keys, int64_t n_keys, int w, int h, int max_corners, double min_distance,
+                                   float* corners, int capacity, int* n_out)
+{
+    if (!n_out || n_keys < 0 || (n_keys > 0 && !keys) || w < 1 || h < 1 || max_corners < 0 || !(min_distance >= 0) ||
+        capacity < 0 || (capacity > 0 && !corners))
+        return KLT_ERR_INVALID_ARG;
+    *n_out = 0;
+    // strongest first; equal values: the larger y * w + x first (OpenCV sorts pointers into the eigenvalue image with
+    // "*a > *b, then a > b") -- both are the descending order of the 64-bit key
+    std::sort(keys, keys + n_keys, std::greater<uint64_t>());
+    int nc = 0;
+    auto emit = [&](int x, int y) {
+        if (nc < capacity) { corners[2 * nc] = (float)x; corners[2 * nc + 1] = (float)y; }
+        ++nc;
+        return max_corners > 0 && nc == max_corners;
+    };
+    if (min_distance >= 1) {
+        // G.8: grid of cells of size cvRound(minDistance); a candidate is dropped if an accepted corner in the 3 x 3
+        // neighbouring cells is closer than minDistance
+        const int cell = (int)std::lrint(min_distance);
+        const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+        const double md2 = min_distance * min_distance;
+        std::vector<int> head;
+        std::vector<int> next;
+        std::vector<float> acc;
+        try {
+            head.assign((size_t)gw * gh, -1);
+            next.reserve(1024);
+            acc.reserve(2048);
+        } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+        for (int64_t i = 0; i < n_keys; ++i) {
+            const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffu);
+            const int y = (int)(idx / (uint32_t)w), x = (int)(idx - (uint32_t)y * (uint32_t)w);
+            if (y >= h) return KLT_ERR_INVALID_ARG;
+            const int xc = x / cell, yc = y / cell;
+            const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
+            bool good = true;
+            for (int yy = y1; yy <= y2 && good; ++yy)
+                for (int xx = x1; xx <= x2 && good; ++xx)
+                    for (int j = head[(size_t)yy * gw + xx]; j >= 0; j = next[j]) {
+                        const float dx = (float)x - acc[2 * j], dy = (float)y - acc[2 * j + 1];
+                        if ((double)(dx * dx + dy * dy) < md2) { good = false; break; }
+                    }
+            if (!good) continue;
+            try {
+                acc.push_back((float)x); acc.push_back((float)y);
+                next.push_back(head[(size_t)yc * gw + xc]);
+            } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+            head[(size_t)yc * gw + xc] = (int)next.size() - 1;
+            if (emit(x, y)) break;
+        }
+    } else {
+        for (int64_t i = 0; i < n_keys; ++i) {
+            const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffu);
+            const int y = (int)(idx / (uint32_t)w), x = (int)(idx - (uint32_t)y * (uint32_t)w);
+            if (emit(x, y)) break;
+        }
+    }
+    *n_out = nc;
+    return KLT_OK;
+}
+
+namespace {
+
+// upload a u8 image: one contiguous DMA in the caller's pitch when the rows are (nearly) packed, else a 2-D copy
+klt_status upload_u8(uint8_t* dst, int64_t* dpitch, const uint8_t* src, int64_t pitch, int w, int h, cudaStream_t st)
+{
+    const size_t raw = (size_t)(h - 1) * (size_t)pitch + (size_t)w;
+    if (raw <= 2 * (size_t)w * (size_t)h) {
+        KLT_CUDA(cudaMemcpyAsync(dst, src, raw, cudaMemcpyHostToDevice, st));
+        *dpitch = pitch;
+    } else {
+        KLT_CUDA(cudaMemcpy2DAsync(dst, (size_t)w, src, (size_t)pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+        *dpitch = w;
+    }
+    return KLT_OK;
+}
+
+size_t upload_bytes(int64_t pitch, int w, int h)
+{
+    const size_t raw = (size_t)(h - 1) * (size_t)pitch + (size_t)w;
+    return align_up(raw <= 2 * (size_t)w * (size_t)h ? raw : (size_t)w * (size_t)h, 256);
+}
+
+}  // namespace
+
+klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h, int block_size,
+                                         float* eig)
+{
+    if (!ctx || !img || !eig || w < 1 || h < 1 || pitch < w || block_size < 1) return KLT_ERR_INVALID_ARG;
+    if (block_size / 2 >= w || block_size / 2 >= h) return KLT_ERR_UNSUPPORTED;
+    KLT_CUDA(cudaSetDevice(ctx->device));
+    const size_t img_bytes = upload_bytes(pitch, w, h);
+    const size_t eig_bytes = align_up((size_t)w * h * 4, 256);
+    const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
+    klt_status s = ensure_device_ws(ctx, img_bytes + eig_bytes + ws_bytes);
+    if (s != KLT_OK) return s;
+    uint8_t* d = ctx->d_ws;
+    cudaStream_t st = ctx->stream;
+    int64_t dpitch = 0;
+    s = upload_u8(d, &dpitch, img, pitch, w, h, st);
+    if (s != KLT_OK) return s;
+    float* d_eig = reinterpret_cast<float*>(d + img_bytes);
+    s = corner_min_eig_launch(d, dpitch, 0, w, h, 1, block_size, d_eig, w, 0, nullptr, 0, 0, nullptr, d + img_bytes + eig_bytes, st);
+    if (s != KLT_OK) return s;
+    KLT_CUDA(cudaMemcpyAsync(eig, d_eig, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
+    KLT_CUDA(cudaStreamSynchronize(st));
+    return KLT_OK;
+}
+
+klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                                           const uint8_t* mask, int64_t mask_pitch, int max_corners, double quality_level,
+                                           double min_distance, int block_size, float* corners, int capacity, int* n_out)
+{
+    if (!ctx || !img || !n_out || w < 1 || h < 1 || pitch < w || block_size < 1 || capacity < 0 || (capacity > 0 && !corners))
+        return KLT_ERR_INVALID_ARG;
+    if (!(quality_level > 0) || !(min_distance >= 0) || max_corners < 0) return KLT_ERR_INVALID_ARG;   // CV_Assert of goodFeaturesToTrack
+    if (mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
+    if (block_size / 2 >= w || block_size / 2 >= h || (int64_t)w * h > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    *n_out = 0;
+    KLT_CUDA(cudaSetDevice(ctx->device));
+    const size_t img_bytes = upload_bytes(pitch, w, h);
+    const size_t mask_bytes = mask ? upload_bytes(mask_pitch, w, h) : 0;
+    const size_t eig_bytes = align_up((size_t)w * h * 4, 256);
+    const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
+    // candidate keys land directly in the context's page-locked, device-mapped staging buffer (no D2H copy op); only
+    // when an image yields more candidates than fit there (plateaus of equal eigenvalues) a device buffer is used
+    const size_t n_px = (size_t)w * h;
+    const size_t direct_cap = std::min<size_t>(n_px, 1u << 16);
+    const size_t off_img = 0, off_mask = off_img + img_bytes, off_eig = off_mask + mask_bytes, off_ws = off_eig + eig_bytes;
+    const size_t off_cnt = off_ws + ws_bytes, off_keys = off_cnt + 256;
+    klt_status s = ensure_device_ws(ctx, off_keys);
+    if (s != KLT_OK) return s;
+    s = ensure_host_ws(ctx, 256 + direct_cap * 8);
+    if (s != KLT_OK) return s;
+    uint8_t* d = ctx->d_ws;
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    unsigned* d_max = reinterpret_cast<unsigned*>(d + off_cnt);
+    unsigned* d_count = d_max + 1;
+    KLT_CUDA(cudaMemsetAsync(d_max, 0, 8, st));
+    int64_t ipitch = 0, mpitch = 0;
+    if (mask) {
+        s = upload_u8(d + off_mask, &mpitch, mask, mask_pitch, w, h, st2);
+        if (s != KLT_OK) return s;
+        KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
+    }
+    s = upload_u8(d + off_img, &ipitch, img, pitch, w, h, st);
+    if (s != KLT_OK) return s;
+    if (mask) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
+    const uint8_t* d_mask = mask ? d + off_mask : nullptr;
+    float* d_eig = reinterpret_cast<float*>(d + off_eig);
+    s = corner_min_eig_launch(d + off_img, ipitch, 0, w, h, 1, block_size, d_eig, w, 0, d_mask, mpitch, 0, d_max, d + off_ws, st);
+    if (s != KLT_OK) return s;
+    const bool direct = ctx->h_ws_dev != nullptr;
+    uint64_t* h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws + 256);
+    size_t cap = direct_cap;
+    if (direct) {
+        s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level,
+                                     reinterpret_cast<unsigned long long*>(ctx->h_ws_dev + 256), 0, (int)cap, d_count, st);
+        if (s != KLT_OK) return s;
+    }
+    unsigned count = 0;
+    if (direct) {
+        KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_count, 4, cudaMemcpyDeviceToHost, st));
+        KLT_CUDA(cudaStreamSynchronize(st));
+        count = *reinterpret_cast<unsigned*>(ctx->h_ws);
+    }
+    if (!direct || count > cap) {
+        // all candidates through a device buffer sized for the worst case (every interior pixel)
+        cap = n_px;
+        s = ensure_device_ws(ctx, off_keys + cap * 8);   // may move the workspace: everything is recomputed below
+        if (s != KLT_OK) return s;
+        s = ensure_host_ws(ctx, 256 + cap * 8);
+        if (s != KLT_OK) return s;
+        if (ctx->d_ws != d) {
+            // the workspace was reallocated (contents lost): run the whole call again now that it is large enough
+            return klt_good_features_to_track_host(ctx, img, pitch, w, h, mask, mask_pitch, max_corners, quality_level,
+                                                   min_distance, block_size, corners, capacity, n_out);
+        }
+        h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws + 256);
+        KLT_CUDA(cudaMemsetAsync(d_count, 0, 4, st));
+        s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level,
+                                     reinterpret_cast<unsigned long long*>(d + off_keys), 0, (int)cap, d_count, st);
+        if (s != KLT_OK) return s;
+        KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_count, 4, cudaMemcpyDeviceToHost, st));
+        KLT_CUDA(cudaStreamSynchronize(st));
+        count = *reinterpret_cast<unsigned*>(ctx->h_ws);
+        if (count > cap) return KLT_ERR_INTERNAL;
+        KLT_CUDA(cudaMemcpyAsync(h_keys, d + off_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+        KLT_CUDA(cudaStreamSynchronize(st));
+    }
+    return klt_select_corners_host(h_keys, (int64_t)count, w, h, max_corners, min_distance, corners, capacity, n_out);
 }
 
 }  // extern "C"

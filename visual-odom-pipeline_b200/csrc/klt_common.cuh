@@ -75,4 +75,15 @@ klt_status track_filter_launch(const float* p0, const float* p1, const float* p0
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream);
 klt_status lk_init(int device);
 
+// Shi-Tomasi detection (klt_corners.cu)
+long long corners_ws_bytes(int w, int h, int batch);
+klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long batch_stride, int w, int h, int batch,
+                                 int block, float* eig, long long eig_pitch, long long eig_batch_stride,
+                                 const uint8_t* mask, long long mask_pitch, long long mask_batch_stride,
+                                 unsigned* max_out, void* ws, cudaStream_t stream);
+klt_status corner_candidates_launch(const float* eig, long long eig_pitch, long long eig_batch_stride, int w, int h, int batch,
+                                    const uint8_t* mask, long long mask_pitch, long long mask_batch_stride,
+                                    const unsigned* max_in, double quality, unsigned long long* keys,
+                                    long long keys_batch_stride, int capacity, unsigned* count, cudaStream_t stream);
+
 }  // namespace klt
