@@ -175,7 +175,7 @@ klt_status klt_corner_min_eigen_val(klt_ctx* ctx, const uint8_t* d_img, int w, i
                         void* d_ws, int64_t ws_bytes, void* stream);
 
 /* Threshold (max * quality_level), 3x3 dilation and local-maximum test of goodFeaturesToTrack fused: appends one
- * 64-bit key per candidate, (order-preserving float encoding << 32) | (y * w + x), in arbitrary order, to d_keys
+ * 64-bit key per candidate, (order-preserving float encoding << 32) | (y << 16) | x, in arbitrary order, to d_keys
  * (capacity keys per batch item, keys_batch_stride in ELEMENTS).  d_count: one uint32 per batch item, zeroed by the
  * caller, receives the number of candidates (may exceed capacity: the excess is dropped). */
 klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_pitch, int64_t eig_batch_stride, int w, int h,
@@ -183,9 +183,9 @@ klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_p
                         const uint32_t* d_max, double quality_level, uint64_t* d_keys, int64_t keys_batch_stride,
                         int capacity, uint32_t* d_count, void* stream);
 
-/* The sequential tail of goodFeaturesToTrack on the HOST: sorts the keys (strongest first, ties by descending
- * y * w + x like OpenCV) in place and runs the greedy minimum-distance selection.  corners: capacity x (x, y) floats;
- * *n_out = corners found (<= max_corners if max_corners > 0). */
+/* The sequential tail of goodFeaturesToTrack on the HOST: sorts the keys of klt_corner_candidates in place (strongest
+ * first, equal values: the later pixel in raster order first, like OpenCV) and runs the greedy minimum-distance
+ * selection.  corners: capacity x (x, y) floats; *n_out = corners found (<= max_corners if max_corners > 0). */
 klt_status klt_select_corners_host(uint64_t* keys, int64_t n_keys, int w, int h, int max_corners, double min_distance,
                         float* corners, int capacity, int* n_out);
 

@@ -543,16 +543,54 @@ klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_p
                                     capacity, d_count, (cudaStream_t)stream);
 }
 
+static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, int w, int h, int max_corners, double min_distance,
+                                 float* corners, int capacity, int* n_out);
+
 klt_status klt_select_corners_host(uint64_t* keys, int64_t n_keys, int w, int h, int max_corners, double min_distance,
                                    float* corners, int capacity, int* n_out)
+{
+    return select_corners(keys, n_keys, false, w, h, max_corners, min_distance, corners, capacity, n_out);
+}
+
+static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, int w, int h, int max_corners, double min_distance,
+                                 float* corners, int capacity, int* n_out)
 {
     if (!n_out || n_keys < 0 || (n_keys > 0 && !keys) || w < 1 || h < 1 || max_corners < 0 || !(min_distance >= 0) ||
         capacity < 0 || (capacity > 0 && !corners))
         return KLT_ERR_INVALID_ARG;
     *n_out = 0;
-    // strongest first; equal values: the larger y * w + x first (OpenCV sorts pointers into the eigenvalue image with
+    // strongest first; equal values: the later pixel in raster order first (OpenCV sorts pointers into the eigenvalue image with
     // "*a > *b, then a > b") -- both are the descending order of the 64-bit key
-    std::sort(keys, keys + n_keys, std::greater<uint64_t>());
+    if (sorted) {
+        // the device already sorted them
+    } else if (n_keys < 256) {
+        std::sort(keys, keys + n_keys, std::greater<uint64_t>());
+    } else {
+        // LSD radix sort on the value half (3 passes of 11 / 11 / 10 bits, descending, stable), then the (rare) runs
+        // of equal values are ordered by descending index
+        std::vector<uint64_t> tmp;
+        try { tmp.resize((size_t)n_keys); } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+        uint64_t* src = keys;
+        uint64_t* dst = tmp.data();
+        const int shift[3] = {32, 43, 54}, bits[3] = {11, 11, 10};
+        for (int p = 0; p < 3; ++p) {
+            const unsigned nb = 1u << bits[p], msk = nb - 1u;
+            unsigned hist[2048] = {0};
+            for (int64_t i = 0; i < n_keys; ++i) ++hist[msk - (unsigned)((src[i] >> shift[p]) & msk)];
+            unsigned run = 0;
+            for (unsigned d = 0; d < nb; ++d) { const unsigned c = hist[d]; hist[d] = run; run += c; }
+            for (int64_t i = 0; i < n_keys; ++i) dst[hist[msk - (unsigned)((src[i] >> shift[p]) & msk)]++] = src[i];
+            std::swap(src, dst);
+        }
+        // three passes: the result is in tmp
+        for (int64_t i = 0; i < n_keys;) {
+            int64_t j = i + 1;
+            while (j < n_keys && (src[j] >> 32) == (src[i] >> 32)) ++j;
+            if (j - i > 1) std::sort(src + i, src + j, std::greater<uint64_t>());
+            i = j;
+        }
+        std::memcpy(keys, src, (size_t)n_keys * 8);
+    }
     int nc = 0;
     auto emit = [&](int x, int y) {
         if (nc < capacity) { corners[2 * nc] = (float)x; corners[2 * nc + 1] = (float)y; }
@@ -565,40 +603,43 @@ klt_status klt_select_corners_host(uint64_t* keys, int64_t n_keys, int w, int h,
         const int cell = (int)std::lrint(min_distance);
         const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
         const double md2 = min_distance * min_distance;
-        std::vector<int> head;
-        std::vector<int> next;
-        std::vector<float> acc;
+        // accepted corners: per-cell singly linked lists in flat arrays (scratch kept per thread across calls)
+        const size_t max_acc = (size_t)((max_corners > 0 && max_corners < n_keys) ? max_corners : n_keys);
+        thread_local std::vector<int> scratch;
         try {
-            head.assign((size_t)gw * gh, -1);
-            next.reserve(1024);
-            acc.reserve(2048);
+            scratch.resize((size_t)gw * gh + 3 * max_acc + 1);
         } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+        int* head = scratch.data();
+        int* next = head + (size_t)gw * gh;
+        int* ax = next + max_acc;
+        int* ay = ax + max_acc;
+        std::fill(head, head + (size_t)gw * gh, -1);
+        int nacc = 0;
+        const double md2c = std::ceil(md2);   // squared pixel distances are integers: d2 < md2  <=>  d2 < ceil(md2)
+        const long long md2i = md2c < 9.0e18 ? (long long)md2c : (long long)9.0e18;
+        // x / cell for 16-bit x by multiplication: exact since x * (cell - 1) < 2^32
+        const uint64_t magic = cell > 1 ? ((1ull << 32) + (uint64_t)cell - 1) / (uint64_t)cell : 0;
         for (int64_t i = 0; i < n_keys; ++i) {
-            const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffu);
-            const int y = (int)(idx / (uint32_t)w), x = (int)(idx - (uint32_t)y * (uint32_t)w);
-            if (y >= h) return KLT_ERR_INVALID_ARG;
-            const int xc = x / cell, yc = y / cell;
+            const int x = (int)(keys[i] & 0xffffu), y = (int)((keys[i] >> 16) & 0xffffu);
+            if (y >= h || x >= w) return KLT_ERR_INVALID_ARG;
+            const int xc = cell > 1 ? (int)(((uint64_t)x * magic) >> 32) : x, yc = cell > 1 ? (int)(((uint64_t)y * magic) >> 32) : y;
             const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
             bool good = true;
             for (int yy = y1; yy <= y2 && good; ++yy)
                 for (int xx = x1; xx <= x2 && good; ++xx)
                     for (int j = head[(size_t)yy * gw + xx]; j >= 0; j = next[j]) {
-                        const float dx = (float)x - acc[2 * j], dy = (float)y - acc[2 * j + 1];
-                        if ((double)(dx * dx + dy * dy) < md2) { good = false; break; }
+                        const long long dx = x - ax[j], dy = y - ay[j];
+                        if (dx * dx + dy * dy < md2i) { good = false; break; }
                     }
             if (!good) continue;
-            try {
-                acc.push_back((float)x); acc.push_back((float)y);
-                next.push_back(head[(size_t)yc * gw + xc]);
-            } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
-            head[(size_t)yc * gw + xc] = (int)next.size() - 1;
+            ax[nacc] = x; ay[nacc] = y;
+            next[nacc] = head[(size_t)yc * gw + xc];
+            head[(size_t)yc * gw + xc] = nacc++;
             if (emit(x, y)) break;
         }
     } else {
         for (int64_t i = 0; i < n_keys; ++i) {
-            const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffu);
-            const int y = (int)(idx / (uint32_t)w), x = (int)(idx - (uint32_t)y * (uint32_t)w);
-            if (emit(x, y)) break;
+            if (emit((int)(keys[i] & 0xffffu), (int)((keys[i] >> 16) & 0xffffu))) break;
         }
     }
     *n_out = nc;
@@ -661,28 +702,27 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
         return KLT_ERR_INVALID_ARG;
     if (!(quality_level > 0) || !(min_distance >= 0) || max_corners < 0) return KLT_ERR_INVALID_ARG;   // CV_Assert of goodFeaturesToTrack
     if (mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
-    if (block_size / 2 >= w || block_size / 2 >= h || (int64_t)w * h > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    if (block_size / 2 >= w || block_size / 2 >= h || w > 65535 || h > 65535) return KLT_ERR_UNSUPPORTED;
     *n_out = 0;
     KLT_CUDA(cudaSetDevice(ctx->device));
     const size_t img_bytes = upload_bytes(pitch, w, h);
     const size_t mask_bytes = mask ? upload_bytes(mask_pitch, w, h) : 0;
     const size_t eig_bytes = align_up((size_t)w * h * 4, 256);
     const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
-    // candidate keys land directly in the context's page-locked, device-mapped staging buffer (no D2H copy op); only
-    // when an image yields more candidates than fit there (plateaus of equal eigenvalues) a device buffer is used
+    // up to direct_cap sorted candidate keys land directly in the context's page-locked, device-mapped staging buffer
     const size_t n_px = (size_t)w * h;
     const size_t direct_cap = std::min<size_t>(n_px, 1u << 16);
     const size_t off_img = 0, off_mask = off_img + img_bytes, off_eig = off_mask + mask_bytes, off_ws = off_eig + eig_bytes;
-    const size_t off_cnt = off_ws + ws_bytes, off_keys = off_cnt + 256;
-    klt_status s = ensure_device_ws(ctx, off_keys);
+    const size_t off_cnt = off_ws + ws_bytes, off_keys = off_cnt + 256 + 8192 * 4;   // max, count, ranks (zeroed per call)
+    klt_status s = ensure_device_ws(ctx, off_keys + (n_px + direct_cap + 1) * 8);
     if (s != KLT_OK) return s;
-    s = ensure_host_ws(ctx, 256 + direct_cap * 8);
+    s = ensure_host_ws(ctx, 8 + direct_cap * 8);
     if (s != KLT_OK) return s;
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     unsigned* d_max = reinterpret_cast<unsigned*>(d + off_cnt);
     unsigned* d_count = d_max + 1;
-    KLT_CUDA(cudaMemsetAsync(d_max, 0, 8, st));
+    KLT_CUDA(cudaMemsetAsync(d_max, 0, 256 + 8192 * 4, st));
     int64_t ipitch = 0, mpitch = 0;
     if (mask) {
         s = upload_u8(d + off_mask, &mpitch, mask, mask_pitch, w, h, st2);
@@ -694,47 +734,49 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
     if (mask) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
     const uint8_t* d_mask = mask ? d + off_mask : nullptr;
     float* d_eig = reinterpret_cast<float*>(d + off_eig);
+    static const bool trace = getenv("KLT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
+    if (trace) cudaStreamSynchronize(st);
+    const auto t1 = now();
     s = corner_min_eig_launch(d + off_img, ipitch, 0, w, h, 1, block_size, d_eig, w, 0, d_mask, mpitch, 0, d_max, d + off_ws, st);
     if (s != KLT_OK) return s;
+    if (trace) cudaStreamSynchronize(st);
+    const auto t2 = now();
+    // candidates -> device list (one slot per pixel: cannot overflow) -> sorted on the device -> written, with their
+    // count, straight into the context's page-locked staging buffer (mapped into the device address space): no copy op
+    unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(d + off_keys);
+    s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level, d_keys, 0, (int)n_px, d_count, st);
+    if (s != KLT_OK) return s;
     const bool direct = ctx->h_ws_dev != nullptr;
-    uint64_t* h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws + 256);
-    size_t cap = direct_cap;
-    if (direct) {
-        s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level,
-                                     reinterpret_cast<unsigned long long*>(ctx->h_ws_dev + 256), 0, (int)cap, d_count, st);
+    unsigned long long* d_out = direct ? reinterpret_cast<unsigned long long*>(ctx->h_ws_dev) : d_keys + n_px;
+    s = corner_sort_launch(d_keys, 0, d_count, 1, reinterpret_cast<unsigned*>(d + off_cnt + 256), d_out, 0, (int)direct_cap, st);
+    if (s != KLT_OK) return s;
+    if (!direct) KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_out, 8 + direct_cap * 8, cudaMemcpyDeviceToHost, st));
+    KLT_CUDA(cudaStreamSynchronize(st));
+    const uint64_t header = *reinterpret_cast<const uint64_t*>(ctx->h_ws);
+    const unsigned count = (unsigned)(header & 0xffffffffu);
+    bool sorted = (header >> 32) & 1;
+    uint64_t* h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws) + 1;
+    if (count > n_px) return KLT_ERR_INTERNAL;
+    if (count > direct_cap) {
+        // more candidates than the staging buffer holds (4K frames, plateaus): copy the whole unsorted list
+        s = ensure_host_ws(ctx, 8 + (size_t)count * 8);   // may move the staging buffer; the device list is untouched
         if (s != KLT_OK) return s;
-    }
-    unsigned count = 0;
-    if (direct) {
-        KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_count, 4, cudaMemcpyDeviceToHost, st));
+        h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws) + 1;
+        KLT_CUDA(cudaMemcpyAsync(h_keys, d_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
         KLT_CUDA(cudaStreamSynchronize(st));
-        count = *reinterpret_cast<unsigned*>(ctx->h_ws);
+        sorted = false;
     }
-    if (!direct || count > cap) {
-        // all candidates through a device buffer sized for the worst case (every interior pixel)
-        cap = n_px;
-        s = ensure_device_ws(ctx, off_keys + cap * 8);   // may move the workspace: everything is recomputed below
-        if (s != KLT_OK) return s;
-        s = ensure_host_ws(ctx, 256 + cap * 8);
-        if (s != KLT_OK) return s;
-        if (ctx->d_ws != d) {
-            // the workspace was reallocated (contents lost): run the whole call again now that it is large enough
-            return klt_good_features_to_track_host(ctx, img, pitch, w, h, mask, mask_pitch, max_corners, quality_level,
-                                                   min_distance, block_size, corners, capacity, n_out);
-        }
-        h_keys = reinterpret_cast<uint64_t*>(ctx->h_ws + 256);
-        KLT_CUDA(cudaMemsetAsync(d_count, 0, 4, st));
-        s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level,
-                                     reinterpret_cast<unsigned long long*>(d + off_keys), 0, (int)cap, d_count, st);
-        if (s != KLT_OK) return s;
-        KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_count, 4, cudaMemcpyDeviceToHost, st));
-        KLT_CUDA(cudaStreamSynchronize(st));
-        count = *reinterpret_cast<unsigned*>(ctx->h_ws);
-        if (count > cap) return KLT_ERR_INTERNAL;
-        KLT_CUDA(cudaMemcpyAsync(h_keys, d + off_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
-        KLT_CUDA(cudaStreamSynchronize(st));
-    }
-    return klt_select_corners_host(h_keys, (int64_t)count, w, h, max_corners, min_distance, corners, capacity, n_out);
+    const auto t3 = now();
+    s = select_corners(h_keys, (int64_t)count, sorted, w, h, max_corners, min_distance, corners, capacity, n_out);
+    if (trace)
+        std::fprintf(stderr, "[klt trace] gftt: h2d done +%.1f us, eigenvalue kernels +%.1f us, candidates + count sync +%.1f us (%u candidates), host sort + selection %.1f us\n",
+                     us(t0, t1), us(t1, t2), us(t2, t3), count, us(t3, now()));
+    return s;
 }
 
 }  // extern "C"

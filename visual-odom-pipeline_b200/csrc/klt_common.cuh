@@ -85,5 +85,10 @@ klt_status corner_candidates_launch(const float* eig, long long eig_pitch, long 
                                     const uint8_t* mask, long long mask_pitch, long long mask_batch_stride,
                                     const unsigned* max_in, double quality, unsigned long long* keys,
                                     long long keys_batch_stride, int capacity, unsigned* count, cudaStream_t stream);
+// sorts each item's keys (descending) when there are at most 8192 (rank: batch * 8192 zeroed words of scratch);
+// out[0] = count | sorted << 32, keys from out[1]
+klt_status corner_sort_launch(const unsigned long long* keys, long long keys_batch_stride, const unsigned* count, int batch,
+                              unsigned* rank, unsigned long long* out, long long out_batch_stride, int out_capacity,
+                              cudaStream_t stream);
 
 }  // namespace klt

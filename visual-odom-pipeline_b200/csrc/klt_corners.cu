@@ -8,12 +8,13 @@
 //   cov_kernel        32x32 pixel tiles: u8 tile + halo in shared memory -> Dx, Dy -> (Dx^2, DxDy, Dy^2), written
 //                     TRANSPOSED ([channel][x][y]) so that the row scan reads it coalesced;
 //   row_scan_kernel   one lane per image row (a warp = 32 rows of one channel): the serial double-precision running
-//                     sum along x (the order is part of the result: the sums are not exact), loads prefetched a chunk
-//                     ahead, results transposed through shared memory and written row-major;
-//   col_scan_kernel   one thread per image column, the three channels as three independent chains: running sum along
-//                     y, float32 conversion, eigenvalue, masked maximum (REDUX + one atomicMax per warp);
+//                     sum along x (the order is part of the result: the sums are not exact); operands staged with
+//                     cp.async several chunks ahead, results transposed through shared memory and written row-major;
+//   col_scan_kernel   one lane per image column, the three channels as three independent chains: running sum along
+//                     y (operand rows staged with cp.async), float32 conversion, eigenvalue, masked maximum (REDUX +
+//                     one atomicMax per warp);
 //   candidates_kernel threshold (maxVal * qualityLevel), 3x3 dilation and local-maximum test fused; survivors are
-//                     appended as 64-bit keys (ordered float << 32 | y*W+x) with one atomicAdd per warp.
+//                     appended as 64-bit keys (ordered float << 32 | y << 16 | x) with one atomicAdd per 32x32 tile.
 // The sort of the (few thousand) keys and the greedy minimum-distance selection (G.8) are inherently sequential
 // and run on the host (klt_capi.cu), like the tail of cv::cuda::GoodFeaturesToTrackDetector.
 #include "klt_common.cuh"
@@ -87,160 +88,400 @@ cov_kernel(const uint8_t* __restrict__ img, long long pitch, long long batch_str
     }
 }
 
+// ---- cp.async helpers (LDGSTS: global -> shared without registers in flight) ------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- row_scan_kernel ------------------------------------------------------------------------------------------
-constexpr int kChunk = 16;
+// The running sum along x is a serial chain of one DADD per pixel and row, and with so little parallelism (H rows x 3
+// channels) the launch time IS the time of one chain.  So the block is specialised: warp 0 ("chain", lane = row) does
+// nothing but  d = smem, s += d, smem = s;  eight helper warps keep everything else off that warp: they stage the two
+// operand columns of each step (entering and leaving the box; each column of the transposed product image is one
+// 128-byte run over the block's 32 rows) with cp.async kRowStages chunks ahead, form d = (double)new - (double)old
+// exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  One __syncthreads per chunk.
+constexpr int kRowChunk = 32;     // x steps per chunk
+constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
+constexpr int kRowThreads = 32 + 256;
+struct RowSmem {
+    float lead[kRowStages][kRowChunk][32];
+    float trail[kRowStages][kRowChunk][32];
+    double d[2][kRowChunk][32];
+    double s[2][32][kRowChunk + 1];
+};
 
 // padded column i (0 <= i < w + block - 1) -> source column (reflect-101 of i - anchor)
 __device__ __forceinline__ int src_col(int i, int an, int w) { return reflect101(i - an, w); }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kRowThreads)
 row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block, double* __restrict__ rows, int wd)
 {
-    __shared__ double sD[32][kChunk + 1];
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
     const int y0 = blockIdx.x * 32, c = blockIdx.y;
-    const int y = min(y0 + lane, h - 1);
     const int an = block / 2;
-    const float* __restrict__ S = covT + ((long long)blockIdx.z * 3 + c) * w * hp + y;   // element x at S[x * hp]
-    double* __restrict__ D = rows + (((long long)blockIdx.z * 3 + c) * h + y0) * wd;      // row r at D + r * wd
+    const float* __restrict__ S0 = covT + ((long long)blockIdx.z * 3 + c) * w * hp + y0;   // column x: 32 floats at S0 + x * hp
+    double* __restrict__ D = rows + (((long long)blockIdx.z * 3 + c) * h + y0) * wd;        // row r at D + r * wd
     const int nrows = min(32, h - y0);
+    const int nck = (w + kRowChunk - 1) / kRowChunk;
+    // output o = 0 is the sum of the first `block` padded columns; output o >= 1 adds column o-1+block and drops o-1
 
-    auto flush = [&](int xbase, int n) {   // write columns [xbase, xbase + n) of the 32 rows, coalesced
-        __syncwarp();
-        for (int r = 0; r < nrows; ++r)
-            if (lane < n) D[(long long)r * wd + xbase + lane] = sD[r][lane];
-        __syncwarp();
-    };
-
-    if (block == 3 || block == 5) {
-        // OpenCV's RowSum forms fresh left-to-right sums for these two kernel sizes
-        for (int xb = 0; xb < w; xb += kChunk) {
-            const int n = min(kChunk, w - xb);
-            for (int j = 0; j < n; ++j) {
-                double s = (double)S[(long long)src_col(xb + j, an, w) * hp];
-                for (int k = 1; k < block; ++k) s = __dadd_rn(s, (double)S[(long long)src_col(xb + j + k, an, w) * hp]);
-                sD[lane][j] = s;
-            }
-            flush(xb, n);
+    if (tid < 32) {
+        // ---- chain warp ----
+        const float* __restrict__ S = S0 + lane;
+        double s = 0.0;
+        for (int i0 = 0; i0 < block; i0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = S[(long long)src_col(min(i0 + i, block - 1), an, w) * hp];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i0 + i < block) s = __dadd_rn(s, (double)v[i]);
+        }
+        __syncthreads();   // chunk 0 converted
+        for (int k = 0; k < nck; ++k) {
+            const double* __restrict__ pd = &sm.d[k & 1][0][lane];
+            double* __restrict__ ps = &sm.s[k & 1][lane][0];
+            // all operands into registers first: the loads must not queue behind the (possibly aliasing) stores
+            double v[kRowChunk];
+#pragma unroll
+            for (int j = 0; j < kRowChunk; ++j) v[j] = pd[j * 32];
+            if (k == 0) v[0] = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
+#pragma unroll
+            for (int j = 0; j < kRowChunk; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
+#pragma unroll
+            for (int j = 0; j < kRowChunk; ++j) ps[j] = v[j];
+            __syncthreads();
         }
         return;
     }
-    double s = 0.0;
-    for (int i = 0; i < block; ++i) s = __dadd_rn(s, (double)S[(long long)src_col(i, an, w) * hp]);
-    // D[0] = s, then D[x + 1] = (s += new - old) for x = 0 .. w - 2: chunk k covers outputs [k*kChunk, (k+1)*kChunk)
-    float lead[kChunk], trail[kChunk];
-    auto fetch = [&](int xb) {   // operands of outputs xb + 1 + j, j = 0 .. kChunk-1 (steps x = xb + j)
-#pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
-            const int x = min(xb + j, w - 2 >= 0 ? w - 2 : 0);
-            lead[j] = S[(long long)src_col(x + block, an, w) * hp];
-            trail[j] = S[(long long)src_col(x, an, w) * hp];
+    // ---- helper warps: thread = one 16-byte piece (4 rows) of every staged column ----
+    const int ht = tid - 32;
+    const int pj = ht >> 3, part = (ht & 7) * 4;   // column within the chunk, first of 4 rows
+    auto issue = [&](int k) {
+        if (k < nck) {
+            const int o = min(max(k * kRowChunk + pj, 1), w - 1 > 1 ? w - 1 : 1);
+            cp_async16(&sm.lead[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1 + block, an, w) * hp + part);
+            cp_async16(&sm.trail[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1, an, w) * hp + part);
+        }
+        cp_async_commit();
+    };
+    auto convert = [&](int k) {   // the pieces this thread staged itself: no cross-thread dependency
+        if (k < nck) {
+            const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
+            const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
+            double2 d0, d1;
+            d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
+            d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
+            double2* dst = reinterpret_cast<double2*>(&sm.d[k & 1][pj][part]);
+            dst[0] = d0; dst[1] = d1;
         }
     };
-    // output 0
-    sD[lane][0] = s;
-    int fill = 1, xbase = 0;   // sD holds outputs [xbase, xbase + fill)
-    for (int xb = 0; xb < w - 1; xb += kChunk) {
-        fetch(xb);
-        const int n = min(kChunk, w - 1 - xb);
+    auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3
+        const int r = ht >> 3, c0 = (ht & 7) * 4;
+        const int xbase = k * kRowChunk, n = min(kRowChunk, w - xbase);
+        if (r < nrows) {
+            const double* __restrict__ ps = &sm.s[k & 1][r][c0];
+            double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
+            if (c0 + 3 < n) {
+                reinterpret_cast<double2*>(dst)[0] = make_double2(ps[0], ps[1]);
+                reinterpret_cast<double2*>(dst)[1] = make_double2(ps[2], ps[3]);
+            } else {
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
-            if (j < n) {
-                s = __dadd_rn(s, __dsub_rn((double)lead[j], (double)trail[j]));
-                sD[lane][fill] = s;
-                if (++fill == kChunk) { flush(xbase, kChunk); xbase += kChunk; fill = 0; }
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + i < n) dst[i] = ps[i];
             }
         }
+    };
+#pragma unroll
+    for (int k = 0; k < kRowStages; ++k) issue(k);
+    cp_async_wait<kRowStages - 1>();
+    convert(0);
+    __syncthreads();
+    for (int k = 0; k < nck; ++k) {
+        if (k >= 1) flush(k - 1);
+        cp_async_wait<kRowStages - 2>();   // chunk k + 1 has landed
+        convert(k + 1);
+        issue(k + kRowStages);             // its slot (chunk k's) was consumed by this thread one iteration ago
+        __syncthreads();
     }
-    if (fill) flush(xbase, fill);
+    flush(nck - 1);
+}
+
+// OpenCV's RowSum forms fresh left-to-right sums for kernel sizes 3 and 5: no chain, one thread per output.
+__global__ void __launch_bounds__(256)
+row_sum_small_kernel(const float* __restrict__ covT, int w, int h, int hp, int block, double* __restrict__ rows, int wd)
+{
+    const int y = blockIdx.x * 32 + threadIdx.x, x = blockIdx.y * 8 + threadIdx.y;
+    const int c = blockIdx.z % 3, b = blockIdx.z / 3;
+    if (x >= w || y >= h) return;
+    const int an = block / 2;
+    const float* __restrict__ S = covT + ((long long)b * 3 + c) * w * hp + y;
+    double s = (double)S[(long long)src_col(x, an, w) * hp];
+    for (int k = 1; k < block; ++k) s = __dadd_rn(s, (double)S[(long long)src_col(x + k, an, w) * hp]);
+    rows[(((long long)b * 3 + c) * h + y) * wd + x] = s;
 }
 
 // ---- col_scan_kernel ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+// Same specialisation along y: warps 0..2 are the chains of the three channels (lane = column; two dependent DADDs
+// per pixel:  t = SUM + entering row,  SUM = t - leaving row), thirteen helper warps stage the entering / leaving
+// row-sum rows with cp.async kColStages-1 chunks ahead and turn the finished box sums of the previous chunk into the
+// eigenvalue (G.6), the masked maximum and the coalesced float32 output.
+constexpr int kColChunk = 16;     // y steps per chunk
+constexpr int kColStages = 4;
+constexpr int kColThreads = 96 + 384, kColHelpers = kColThreads - 96;
+struct ColSmem {
+    double st[kColStages][2][3][kColChunk][32];   // [stage][entering / leaving][channel][row][column]
+    float t[2][3][kColChunk][32];
+};
+
+__global__ void __launch_bounds__(kColThreads)
 col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block, float* __restrict__ eig, long long eig_pitch,
                 long long eig_batch_stride, const uint8_t* __restrict__ mask, long long mask_pitch, long long mask_batch_stride,
                 unsigned* __restrict__ max_out)
 {
-    const int x = blockIdx.x * 64 + threadIdx.x;
-    const int xc = min(x, w - 1);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ColSmem& sm = *reinterpret_cast<ColSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int x0 = blockIdx.x * 32;
     const int an = block / 2;
     const long long plane = (long long)h * wd;
-    const double* __restrict__ R0 = rows + (long long)blockIdx.z * 3 * plane + xc;
-    const double* __restrict__ R1 = R0 + plane;
-    const double* __restrict__ R2 = R1 + plane;
+    const double* __restrict__ R = rows + (long long)blockIdx.z * 3 * plane + x0;
+    const int nck = (h + kColChunk - 1) / kColChunk;
+
+    if (wrp < 3) {
+        // ---- chain warps ----
+        const double* __restrict__ Rx = R + wrp * plane + lane;
+        double s = 0.0;
+        for (int i0 = 0; i0 < block - 1; i0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = Rx[(long long)reflect101(min(i0 + i, block - 2) - an, h) * wd];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i0 + i < block - 1) s = __dadd_rn(s, v[i]);
+        }
+        __syncthreads();   // chunk 0 staged
+        for (int k = 0; k < nck; ++k) {
+            const double* __restrict__ pe = &sm.st[k % kColStages][0][wrp][0][lane];
+            const double* __restrict__ pl = &sm.st[k % kColStages][1][wrp][0][lane];
+            float* __restrict__ pt = &sm.t[k & 1][wrp][0][lane];
+            double ve[kColChunk], vl[kColChunk];   // operands into registers first (see row_scan_kernel)
+#pragma unroll
+            for (int j = 0; j < kColChunk; ++j) { ve[j] = pe[j * 32]; vl[j] = pl[j * 32]; }
+#pragma unroll
+            for (int j = 0; j < kColChunk; ++j) {
+                ve[j] = __dadd_rn(s, ve[j]);
+                s = __dsub_rn(ve[j], vl[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kColChunk; ++j) pt[j * 32] = __double2float_rn(ve[j]);
+            __syncthreads();
+        }
+        return;
+    }
+    // ---- helper warps: every thread owns 4 fixed 16-byte pieces of each stage and up to 2 pixels of each chunk ----
+    const int ht = tid - 96;
     float* __restrict__ E = eig + (long long)blockIdx.z * eig_batch_stride;
     const uint8_t* __restrict__ M = mask ? mask + (long long)blockIdx.z * mask_batch_stride : nullptr;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < block - 1; ++i) {
-        const long long o = (long long)reflect101(i - an, h) * wd;
-        s0 = __dadd_rn(s0, R0[o]); s1 = __dadd_rn(s1, R1[o]); s2 = __dadd_rn(s2, R2[o]);
-    }
+    static_assert(2 * 3 * kColChunk * 16 == 4 * kColHelpers, "4 pieces per helper thread");
+    const int part2 = (ht & 15) * 2;                   // piece = 2 doubles of a 32-column row
+    const int pp = (ht >> 4) % 6, prg = (ht >> 4) / 6;  // plane (entering / leaving x channel), row group 0..3
+    const int plt = pp / 3, pc = pp - 3 * plt;
+    const double* __restrict__ Rp = R + pc * plane + part2;
+    auto issue = [&](int k) {   // rows entering (y + block - 1 - an) and leaving (y - an) for y in chunk k
+        if (k < nck) {
+            double* st = &sm.st[k % kColStages][plt][pc][0][part2];
+#pragma unroll
+            for (int i = 0; i < kColChunk / 4; ++i) {
+                const int r = prg + 4 * i;
+                const int y = min(k * kColChunk + r, h - 1);
+                const int sy = reflect101(plt ? y - an : y + block - 1 - an, h);
+                cp_async16(st + r * 32, Rp + (long long)sy * wd);
+            }
+        }
+        cp_async_commit();
+    };
     unsigned best = 0;   // 0 = nothing seen (every real float maps above it)
-#pragma unroll 4
-    for (int y = 0; y < h; ++y) {
-        const long long op = (long long)reflect101(y + block - 1 - an, h) * wd;
-        const long long om = (long long)reflect101(y - an, h) * wd;
-        const double p0 = R0[op], p1 = R1[op], p2 = R2[op];
-        const double m0 = R0[om], m1 = R1[om], m2 = R2[om];
-        const double t0 = __dadd_rn(s0, p0), t1 = __dadd_rn(s1, p1), t2 = __dadd_rn(s2, p2);
-        s0 = __dsub_rn(t0, m0); s1 = __dsub_rn(t1, m1); s2 = __dsub_rn(t2, m2);
-        const float a = __fmul_rn(__double2float_rn(t0), 0.5f), b = __double2float_rn(t1), c = __fmul_rn(__double2float_rn(t2), 0.5f);
+    const int fj0 = ht >> 5, fx = ht & 31;   // pixels (row fj0, column fx) and (row fj0 + kColHelpers / 32, column fx) of a chunk
+    auto load_mask = [&](int k, unsigned& m0, unsigned& m1) {
+        m0 = 1u; m1 = 1u;
+        if (M && k < nck) {
+            const int x = x0 + fx, ya = k * kColChunk + fj0, yb = ya + kColHelpers / 32;
+            if (x < w && ya < h) m0 = M[(long long)ya * mask_pitch + x];
+            if (x < w && yb < h && fj0 + kColHelpers / 32 < kColChunk) m1 = M[(long long)yb * mask_pitch + x];
+        }
+    };
+    auto finish_px = [&](int k, int j, unsigned m) {
+        const int y = k * kColChunk + j, x = x0 + fx;
+        const float a = __fmul_rn(sm.t[k & 1][0][j][fx], 0.5f), b = sm.t[k & 1][1][j][fx], c = __fmul_rn(sm.t[k & 1][2][j][fx], 0.5f);
         const float d = __fsub_rn(a, c);
         const float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));   // G.6
-        if (x < w) {
+        if (x < w && y < h) {
             E[(long long)y * eig_pitch + x] = e;
-            if (max_out && (!M || M[(long long)y * mask_pitch + x])) best = max(best, ordered_from_float(e));
+            if (max_out && m) best = max(best, ordered_from_float(e));
         }
+    };
+    auto finish = [&](int k, unsigned m0, unsigned m1) {  // eigenvalues of chunk k
+        finish_px(k, fj0, m0);
+        if (fj0 + kColHelpers / 32 < kColChunk) finish_px(k, fj0 + kColHelpers / 32, m1);
+    };
+#pragma unroll
+    for (int k = 0; k < kColStages - 1; ++k) issue(k);
+    cp_async_wait<kColStages - 2>();
+    __syncthreads();
+    unsigned mc0 = 1u, mc1 = 1u;
+    for (int k = 0; k < nck; ++k) {
+        issue(k + kColStages - 1);          // into the slot of chunk k - 1, consumed before the last barrier
+        unsigned mn0, mn1;
+        load_mask(k, mn0, mn1);             // consumed one iteration later: the load latency hides behind the barrier
+        if (k >= 1) finish(k - 1, mc0, mc1);
+        cp_async_wait<kColStages - 2>();    // chunk k + 1 has landed
+        __syncthreads();
+        mc0 = mn0; mc1 = mn1;
     }
+    finish(nck - 1, mc0, mc1);
     if (max_out) {
         best = __reduce_max_sync(kFullMask, best);
-        if ((threadIdx.x & 31) == 0 && best) atomicMax(max_out + blockIdx.z, best);
+        if (lane == 0 && best) atomicMax(max_out + blockIdx.z, best);
     }
 }
 
 // ---- candidates_kernel ----------------------------------------------------------------------------------------
+// 32 x 32 pixel tile per block (4 rows per thread); the tile's candidates are counted first so that the block takes
+// its slots in the output list with ONE atomicAdd.
 __global__ void __launch_bounds__(256)
 candidates_kernel(const float* __restrict__ eig, long long eig_pitch, long long eig_batch_stride, int w, int h,
                   const uint8_t* __restrict__ mask, long long mask_pitch, long long mask_batch_stride,
                   const unsigned* __restrict__ max_in, double quality, unsigned long long* __restrict__ keys,
                   long long keys_batch_stride, int capacity, unsigned* __restrict__ count)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
+    __shared__ unsigned sWarp[8];
+    __shared__ unsigned sBase;
+    const int lane = threadIdx.x, wrp = threadIdx.y;
+    const int x = blockIdx.x * 32 + lane;
     const int b = blockIdx.z;
     const unsigned mo = max_in[b];
-    const float max_val = mo ? float_from_ordered(mo) : 0.f;                 // minMaxLoc over an empty mask gives 0
+    const float max_val = mo ? float_from_ordered(mo) : 0.f;                    // minMaxLoc over an empty mask gives 0
     const float thr = __double2float_rn(__dmul_rn((double)max_val, quality));   // G.7
-    bool is_cand = false;
-    float v = 0.f;
-    if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-        const float* __restrict__ E = eig + (long long)b * eig_batch_stride + (long long)y * eig_pitch + x;
-        v = E[0];
-        v = v > thr ? v : 0.f;
-        if (v != 0.f && (!mask || mask[(long long)b * mask_batch_stride + (long long)y * mask_pitch + x])) {
-            float m = v;
+    float val[4];
+    unsigned cand = 0;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
+    for (int k = 0; k < 4; ++k) {
+        const int y = blockIdx.y * 32 + wrp * 4 + k;
+        val[k] = 0.f;
+        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+            const float* __restrict__ E = eig + (long long)b * eig_batch_stride + (long long)y * eig_pitch + x;
+            float v = E[0];
+            v = v > thr ? v : 0.f;
+            if (v != 0.f && (!mask || mask[(long long)b * mask_batch_stride + (long long)y * mask_pitch + x])) {
+                float m = v;
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    float u = E[(long long)dy * eig_pitch + dx];
-                    u = u > thr ? u : 0.f;
-                    m = fmaxf(m, u);
-                }
-            is_cand = (v == m);
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        float u = E[(long long)dy * eig_pitch + dx];
+                        u = u > thr ? u : 0.f;
+                        m = fmaxf(m, u);
+                    }
+                if (v == m) { cand |= 1u << k; val[k] = v; }
+            }
         }
     }
-    const unsigned ballot = __ballot_sync(kFullMask, is_cand);
-    if (ballot) {
-        const int lane = threadIdx.x;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(count + b, (unsigned)__popc(ballot));
-        base = __shfl_sync(kFullMask, base, 0);
-        if (is_cand) {
-            const unsigned slot = base + __popc(ballot & ((1u << lane) - 1u));
+    const int mine = __popc(cand);
+    // exclusive prefix of `mine` over the block: warp scan + 8 warp totals
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sWarp[wrp] = (unsigned)incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned t = sWarp[i];
+        before += (i < wrp) ? t : 0u;
+        total += t;
+    }
+    if (total == 0) return;
+    if (lane == 0 && wrp == 0) sBase = atomicAdd(count + b, total);
+    __syncthreads();
+    unsigned slot = sBase + before + (unsigned)(incl - mine);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cand & (1u << k)) {
+            const int y = blockIdx.y * 32 + wrp * 4 + k;
             if (slot < (unsigned)capacity)
-                keys[(long long)b * keys_batch_stride + slot] = ((unsigned long long)ordered_from_float(v) << 32) | (unsigned)(y * w + x);
+                keys[(long long)b * keys_batch_stride + slot] = ((unsigned long long)ordered_from_float(val[k]) << 32) | ((unsigned)y << 16) | (unsigned)x;
+            ++slot;
         }
+}
+
+// ---- rank_keys_kernel / scatter_keys_kernel ------------------------------------------------------------------
+// Sorting a few thousand 64-bit keys on ONE SM is issue-bound (a shared-memory bitonic sort of 8192 keys measured
+// 82 us); the whole chip does it by brute force in a few microseconds: the keys are distinct, so the position of key i
+// in the descending order is the number of keys greater than it.  Block (bi, bj) counts, for 256 keys i, how many of
+// the 1024 keys of chunk bj are greater (chunk in shared memory, broadcast reads) and adds the partial count to
+// rank[i]; a second small kernel writes every key to its position -- straight into page-locked host memory mapped into
+// the device address space when `out` points there, together with a one-word header (count | sorted << 32).  More
+// than kSortMax candidates (plateaus of equal eigenvalues, 4K frames) are passed through unsorted (sorted = 0) and
+// the host sorts them.
+constexpr int kSortMax = 8192;
+constexpr int kRankI = 256, kRankJ = 512;
+
+__global__ void __launch_bounds__(kRankI / 2)
+rank_keys_kernel(const unsigned long long* __restrict__ keys, long long keys_batch_stride, const unsigned* __restrict__ count,
+                 unsigned* __restrict__ rank)
+{
+    __shared__ unsigned long long sj[kRankJ];
+    const int b = blockIdx.z;
+    const int n = (int)count[b];
+    const int i0 = blockIdx.x * kRankI, j0 = blockIdx.y * kRankJ;
+    if (n > kSortMax || i0 >= n || j0 >= n) return;
+    const unsigned long long* __restrict__ src = keys + (long long)b * keys_batch_stride;
+    for (int j = threadIdx.x; j < kRankJ; j += kRankI / 2) sj[j] = (j0 + j < n) ? src[j0 + j] : 0ull;   // 0 is below every key
+    __syncthreads();
+    // two keys per thread: one broadcast shared-memory load feeds two comparisons
+    const int ia = i0 + threadIdx.x, ib = ia + kRankI / 2;
+    const unsigned long long ka = (ia < n) ? src[ia] : ~0ull, kb = (ib < n) ? src[ib] : ~0ull;
+    unsigned above_a = 0, above_b = 0;
+#pragma unroll 16
+    for (int j = 0; j < kRankJ; ++j) {
+        const unsigned long long v = sj[j];
+        above_a += (v > ka) ? 1u : 0u;
+        above_b += (v > kb) ? 1u : 0u;
+    }
+    if (ia < n && above_a) atomicAdd(rank + (long long)b * kSortMax + ia, above_a);
+    if (ib < n && above_b) atomicAdd(rank + (long long)b * kSortMax + ib, above_b);
+}
+
+// one block per image: keys to their positions in shared memory, then out in contiguous runs
+__global__ void __launch_bounds__(1024)
+scatter_keys_kernel(const unsigned long long* __restrict__ keys, long long keys_batch_stride, const unsigned* __restrict__ count,
+                    const unsigned* __restrict__ rank, unsigned long long* __restrict__ out, long long out_batch_stride, int out_capacity)
+{
+    extern __shared__ __align__(16) unsigned long long sk[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned total = count[b];
+    const unsigned long long* __restrict__ src = keys + (long long)b * keys_batch_stride;
+    unsigned long long* __restrict__ dst = out + (long long)b * out_batch_stride;   // dst[0] = header, keys from dst[1]
+    const bool sorted = total <= (unsigned)kSortMax;
+    const int n_out = (int)min(total, (unsigned)out_capacity);
+    if (tid == 0) dst[0] = (unsigned long long)total | (sorted ? (1ull << 32) : 0ull);
+    if (sorted) {
+        for (int i = tid; i < (int)total; i += 1024) sk[rank[(long long)b * kSortMax + i]] = src[i];
+        __syncthreads();
+        for (int i = tid; i < n_out; i += 1024) dst[1 + i] = sk[i];
+    } else {
+        for (int i = tid; i < n_out; i += 1024) dst[1 + i] = src[i];
     }
 }
 
@@ -248,7 +489,7 @@ candidates_kernel(const float* __restrict__ eig, long long eig_pitch, long long 
 
 long long corners_ws_bytes(int w, int h, int batch)
 {
-    const long long hp = (h + 31) / 32 * 32, wd = (w + 3) / 4 * 4;
+    const long long hp = (h + 31) / 32 * 32, wd = (w + 31) / 32 * 32;
     const long long cov = 3LL * w * hp * 4, rows = 3LL * h * wd * 8;
     return ((cov + 255) / 256 * 256 + (rows + 255) / 256 * 256) * batch;
 }
@@ -259,8 +500,8 @@ klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long 
                                  unsigned* max_out, void* ws, cudaStream_t stream)
 {
     if (w < 1 || h < 1 || batch < 1 || block < 1) return KLT_ERR_INVALID_ARG;
-    if (block / 2 >= w || block / 2 >= h || batch > 65535) return KLT_ERR_UNSUPPORTED;
-    const int hp = (h + 31) / 32 * 32, wd = (w + 3) / 4 * 4;
+    if (block / 2 >= w || block / 2 >= h || batch > 21845 || (w + 7) / 8 > 65535) return KLT_ERR_UNSUPPORTED;
+    const int hp = (h + 31) / 32 * 32, wd = (w + 31) / 32 * 32;
     const long long cov_bytes = (3LL * w * hp * 4 * batch + 255) / 256 * 256;
     float* covT = static_cast<float*>(ws);
     double* rows = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + cov_bytes);
@@ -268,9 +509,19 @@ klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long 
     const float k0 = (float)(2.0 / (4.0 * (double)block * 255.0));
     cov_kernel<<<dim3((w + kTile - 1) / kTile, (h + kTile - 1) / kTile, batch), dim3(32, 8), 0, stream>>>(
         img, pitch, batch_stride, w, h, covT, hp, k1, k0);
-    row_scan_kernel<<<dim3((h + 31) / 32, 3, batch), 32, 0, stream>>>(covT, w, h, hp, block, rows, wd);
-    col_scan_kernel<<<dim3((w + 63) / 64, 1, batch), 64, 0, stream>>>(rows, w, h, wd, block, eig, eig_pitch, eig_batch_stride,
-                                                                       mask, mask_pitch, mask_batch_stride, max_out);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(row_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowSmem));
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(col_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColSmem));
+        if (ce != cudaSuccess) return (klt_status)ce;
+        configured = true;
+    }
+    if (block == 3 || block == 5)
+        row_sum_small_kernel<<<dim3((h + 31) / 32, (w + 7) / 8, 3 * batch), dim3(32, 8), 0, stream>>>(covT, w, h, hp, block, rows, wd);
+    else
+        row_scan_kernel<<<dim3((h + 31) / 32, 3, batch), kRowThreads, sizeof(RowSmem), stream>>>(covT, w, h, hp, block, rows, wd);
+    col_scan_kernel<<<dim3((w + 31) / 32, 1, batch), kColThreads, sizeof(ColSmem), stream>>>(rows, w, h, wd, block, eig, eig_pitch, eig_batch_stride,
+                                                                                         mask, mask_pitch, mask_batch_stride, max_out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
@@ -281,10 +532,28 @@ klt_status corner_candidates_launch(const float* eig, long long eig_pitch, long 
                                     long long keys_batch_stride, int capacity, unsigned* count, cudaStream_t stream)
 {
     if (w < 1 || h < 1 || batch < 1 || capacity < 0 || !(quality > 0)) return KLT_ERR_INVALID_ARG;
-    if (batch > 65535 || (long long)w * h > 0xffffffffLL) return KLT_ERR_UNSUPPORTED;
-    candidates_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, batch), dim3(32, 8), 0, stream>>>(
+    if (batch > 65535 || w > 65535 || h > 65535) return KLT_ERR_UNSUPPORTED;
+    candidates_kernel<<<dim3((w + 31) / 32, (h + 31) / 32, batch), dim3(32, 8), 0, stream>>>(
         eig, eig_pitch, eig_batch_stride, w, h, mask, mask_pitch, mask_batch_stride, max_in, quality, keys, keys_batch_stride,
         capacity, count);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+klt_status corner_sort_launch(const unsigned long long* keys, long long keys_batch_stride, const unsigned* count, int batch,
+                              unsigned* rank, unsigned long long* out, long long out_batch_stride, int out_capacity,
+                              cudaStream_t stream)
+{
+    if (batch < 1 || batch > 65535 || out_capacity < 0) return KLT_ERR_INVALID_ARG;
+    // rank: batch * 8192 words, zeroed by the caller
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(scatter_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * 8);
+        if (ce != cudaSuccess) return (klt_status)ce;
+        configured = true;
+    }
+    rank_keys_kernel<<<dim3(kSortMax / kRankI, kSortMax / kRankJ, batch), kRankI / 2, 0, stream>>>(keys, keys_batch_stride, count, rank);
+    scatter_keys_kernel<<<batch, 1024, kSortMax * 8, stream>>>(keys, keys_batch_stride, count, rank, out, out_batch_stride, out_capacity);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
