@@ -45,6 +45,35 @@ def main():
                         top_win21_max8=top, scharr_x=cv2.Scharr(img, cv2.CV_16S, 1, 0), scharr_y=cv2.Scharr(img, cv2.CV_16S, 0, 1),
                         cv2_version=cv2.__version__)
     print("pyramid top", top)
+    make_gftt()
+
+
+GFTT_CASES = {
+    # name: (h, w, seed, blockSize, maxCorners, qualityLevel, minDistance, n_mask_discs)
+    "gftt_reference": (144, 192, 31, 31, 1000, 0.03, 10, 12),   # extractor.py:21-24 parameters, mask as in :102-107
+    "gftt_default":   (120, 161, 32, 3, 0, 0.01, 3.5, 0),       # cv2 defaults: blockSize 3, no mask, no corner limit
+    "gftt_even_block": (96, 128, 33, 4, 40, 0.05, 0, 6),        # even block, no minimum distance, maxCorners binding
+    "gftt_block5":    (90, 70, 34, 5, 200, 0.001, 25, 3),       # fresh-sum row filter of OpenCV (block 3 / 5), large distance
+}
+
+
+def make_gftt():
+    """Detection step: cv2.cornerMinEigenVal / cv2.goodFeaturesToTrack outputs."""
+    for name, (h, w, seed, bs, mc, ql, md, discs) in GFTT_CASES.items():
+        img = S.frame_pair(h, w, seed=seed)[0]
+        rng = np.random.default_rng(seed)
+        mask = None
+        if discs:
+            mask = np.full(img.shape, 255, np.uint8)
+            for _ in range(discs):
+                cv2.circle(mask, (int(rng.integers(0, w)), int(rng.integers(0, h))), 10, 0, -1)
+        eig = cv2.cornerMinEigenVal(img, bs, ksize=3)
+        c = cv2.goodFeaturesToTrack(img, mc, ql, md, mask=mask, blockSize=bs)
+        c = np.zeros((0, 1, 2), np.float32) if c is None else c
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), img=img, mask=np.zeros((0, 0), np.uint8) if mask is None else mask,
+                            eig=eig, corners=c, blockSize=bs, maxCorners=mc, qualityLevel=ql, minDistance=md,
+                            cv2_version=cv2.__version__)
+        print(name, "corners", len(c))
 
 
 if __name__ == "__main__":

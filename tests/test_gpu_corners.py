@@ -1,0 +1,135 @@
+"""GPU tier (pytest -m gpu, B200) of the detection step: the CUDA path, called through
+the C ABI, against the committed golden vectors, the C oracle and live cv2.goodFeaturesToTrack /
+cv2.cornerMinEigenVal (the reference's implementation, src/extractor/extractor.py:110-111) on the same inputs.
+
+Bar: the eigenvalue map is bit-exact (float32 compared as uint32) and the returned corners are identical in
+value AND order (integer pixel coordinates, strongest first)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from visual_odom_pipeline_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cv2():
+    return pytest.importorskip("cv2")
+
+
+def discs_mask(cv2, shape, n, seed, radius=10):
+    rng = np.random.default_rng(seed)
+    m = np.full(shape, 255, np.uint8)
+    for _ in range(n):
+        cv2.circle(m, (int(rng.integers(0, shape[1])), int(rng.integers(0, shape[0]))), radius, 0, -1)
+    return m
+
+
+def same(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def assert_eig_equal(got, want):
+    bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+    assert bad.size == 0, "%d / %d eigenvalues differ; first at %s: %r vs %r" % (len(bad), got.size, bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
+
+
+@pytest.mark.parametrize("name", ["gftt_reference", "gftt_default", "gftt_even_block", "gftt_block5"])
+def test_detection_matches_golden(klt, name):
+    g = load_golden(name)
+    img, bs = g["img"], int(g["blockSize"])
+    mask = g["mask"] if g["mask"].size else None
+    assert_eig_equal(klt.cornerMinEigenVal(img, bs), g["eig"])
+    c = klt.goodFeaturesToTrack(img, int(g["maxCorners"]), float(g["qualityLevel"]), float(g["minDistance"]), mask=mask, blockSize=bs)
+    assert same(c, g["corners"] if len(g["corners"]) else None)
+
+
+@pytest.mark.parametrize("hw", [(376, 1241), (480, 640), (768, 1024), (100, 101), (57, 43), (64, 96), (33, 200)])
+@pytest.mark.parametrize("bs", [31, 3, 5, 7, 4])
+def test_detection_bit_exact_vs_oracle_and_cv2(klt, oracle, cv2, hw, bs):
+    if bs // 2 >= min(hw):
+        pytest.skip("block larger than the image")
+    img = S.frame_pair(hw[0], hw[1], seed=hw[1] + bs)[0]
+    got = klt.cornerMinEigenVal(img, bs)
+    assert_eig_equal(got, cv2.cornerMinEigenVal(img, bs, ksize=3))
+    if hw[0] * hw[1] <= 640 * 480:
+        assert_eig_equal(got, oracle.corner_min_eigen_val(img, bs))
+    mask = discs_mask(cv2, img.shape, 30, bs)
+    for (mc, ql, md, m) in [(1000, 0.03, 10, mask), (1000, 0.03, 7, None), (0, 0.01, 3.5, mask), (50, 0.2, 0, None), (200, 0.001, 25, mask)]:
+        c = klt.goodFeaturesToTrack(img, mc, ql, md, mask=m, blockSize=bs)
+        k = cv2.goodFeaturesToTrack(img, mc, ql, md, mask=m, blockSize=bs)
+        assert same(c, k), "corners differ for maxCorners=%d quality=%g minDistance=%g mask=%s" % (mc, ql, md, m is not None)
+
+
+def test_reference_call_pattern_extract(klt, cv2):
+    """src/extractor/extractor.py:102-111: mask = 255 with a filled circle of radius mask_radius around every tracked
+    keypoint, then goodFeaturesToTrack(img, mask=mask, maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)."""
+    params = dict(maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)   # extractor.py:21-24, min_kp_dist=10
+    img = S.frame_pair(376, 1241, seed=9)[0]
+    tracked = S.uniform_points(400, 376, 1241, seed=10).reshape(-1, 2)
+    mask = np.zeros_like(img)
+    mask[:] = 255
+    for x, y in [np.int32(p) for p in tracked]:
+        cv2.circle(mask, (int(x), int(y)), 10, 0, -1)
+    kp = klt.goodFeaturesToTrack(img.copy(), mask=mask, **params)
+    ref = cv2.goodFeaturesToTrack(img.copy(), mask=mask, **params)
+    assert same(kp, ref) and kp.shape[1:] == (1, 2) and kp.dtype == np.float32
+    # every corner respects the mask and the minimum distance
+    xy = kp.reshape(-1, 2).astype(int)
+    assert (mask[xy[:, 1], xy[:, 0]] != 0).all()
+    d = np.linalg.norm(kp.reshape(-1, 1, 2) - kp.reshape(1, -1, 2), axis=-1) + np.eye(len(kp)) * 1e9
+    assert d.min() >= 10
+
+
+def test_detection_edge_cases(klt, cv2):
+    flat = np.full((60, 80), 77, np.uint8)
+    assert klt.goodFeaturesToTrack(flat, 100, 0.01, 5, blockSize=7) is None
+    img = S.frame_pair(60, 80, seed=4)[0]
+    assert klt.goodFeaturesToTrack(img, 100, 0.01, 5, mask=np.zeros(img.shape, np.uint8), blockSize=7) is None
+    # non-contiguous views (cv2 accepts any strides)
+    big = S.frame_pair(120, 200, seed=5)[0]
+    view, mview = big[::2, 10:170], discs_mask(cv2, big.shape, 10, 1)[::2, 10:170]
+    assert same(klt.goodFeaturesToTrack(view, 200, 0.02, 6, mask=mview, blockSize=9), cv2.goodFeaturesToTrack(view, 200, 0.02, 6, mask=mview, blockSize=9))
+    # (h, w, 1) image, inputs not mutated
+    keep = img.copy()
+    assert same(klt.goodFeaturesToTrack(img[:, :, None], 50, 0.01, 3, blockSize=5), cv2.goodFeaturesToTrack(img, 50, 0.01, 3, blockSize=5))
+    assert np.array_equal(img, keep)
+
+
+def test_plateaus_and_many_candidates(klt, cv2):
+    """Periodic pattern: thousands of candidates with exactly equal eigenvalues -> tie order (later pixel first), the
+    unsorted pass-through of the device sort (> 8192 keys) and the host radix sort."""
+    per = np.tile(np.array([[0, 255], [255, 0]], np.uint8).repeat(8, 0).repeat(8, 1), (40, 60))
+    assert per.shape == (640, 960)
+    for md in (0, 4, 9.5):
+        c = klt.goodFeaturesToTrack(per, 0, 0.01, md, blockSize=3)
+        k = cv2.goodFeaturesToTrack(per, 0, 0.01, md, blockSize=3)
+        assert same(c, k) and len(c) > (8192 if md == 0 else 100)
+    assert_eig_equal(klt.cornerMinEigenVal(per, 3), cv2.cornerMinEigenVal(per, 3, ksize=3))
+
+
+def test_full_size_stress_frame(klt, cv2):
+    """BASELINE configs[4] frame shape (3840 x 2160): more candidates than the mapped staging buffer holds."""
+    img = S.frame_pair(2160, 3840, seed=3)[0]
+    assert_eig_equal(klt.cornerMinEigenVal(img, 31), cv2.cornerMinEigenVal(img, 31, ksize=3))
+    for (mc, ql, md) in [(1000, 0.03, 10), (0, 0.01, 3.5)]:
+        assert same(klt.goodFeaturesToTrack(img, mc, ql, md, blockSize=31), cv2.goodFeaturesToTrack(img, mc, ql, md, blockSize=31))
+
+
+def test_batched_device_api_equals_per_frame_host_calls(klt, cv2):
+    import torch
+    from visual_odom_pipeline_b200 import detector as D, tracker as T
+    B, H, W = 5, 188, 621
+    frames = [S.frame_pair(H, W, seed=80 + i)[0] for i in range(B)]
+    masks = [discs_mask(cv2, (H, W), 20, i) for i in range(B)]
+    dev = T.alloc_image_batch(B, H, W); dev.copy_(torch.from_numpy(np.stack(frames)))
+    dmask = torch.from_numpy(np.stack(masks)).cuda()
+    eig = D.corner_min_eigen_val(dev, 31)
+    res = D.good_features_to_track(dev, 500, 0.03, 10, mask=dmask, blockSize=31)
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert_eig_equal(eig[b].cpu().numpy(), cv2.cornerMinEigenVal(frames[b], 31, ksize=3))
+        assert same(res[b], cv2.goodFeaturesToTrack(frames[b], 500, 0.03, 10, mask=masks[b], blockSize=31)), "frame %d" % b

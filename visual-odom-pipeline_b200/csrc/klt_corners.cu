@@ -105,7 +105,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // operand columns of each step (entering and leaving the box; each column of the transposed product image is one
 // 128-byte run over the block's 32 rows) with cp.async kRowStages chunks ahead, form d = (double)new - (double)old
 // exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  One __syncthreads per chunk.
-constexpr int kRowChunk = 32;     // x steps per chunk
+constexpr int kRowChunk = 64;     // x steps per chunk (multiple of 32)
 constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
 constexpr int kRowThreads = 32 + 256;
 struct RowSmem {
@@ -161,41 +161,54 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
         }
         return;
     }
-    // ---- helper warps: thread = one 16-byte piece (4 rows) of every staged column ----
+    // ---- helper warps: thread = 16-byte pieces (4 rows) of kRowChunk / 32 staged columns ----
     const int ht = tid - 32;
-    const int pj = ht >> 3, part = (ht & 7) * 4;   // column within the chunk, first of 4 rows
+    const int pj0 = ht >> 3, part = (ht & 7) * 4;   // first column within the chunk, first of 4 rows
+    constexpr int NP = kRowChunk / 32;
     auto issue = [&](int k) {
         if (k < nck) {
-            const int o = min(max(k * kRowChunk + pj, 1), w - 1 > 1 ? w - 1 : 1);
-            cp_async16(&sm.lead[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1 + block, an, w) * hp + part);
-            cp_async16(&sm.trail[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1, an, w) * hp + part);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int pj = pj0 + 32 * i;
+                const int o = min(max(k * kRowChunk + pj, 1), w - 1 > 1 ? w - 1 : 1);
+                cp_async16(&sm.lead[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1 + block, an, w) * hp + part);
+                cp_async16(&sm.trail[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1, an, w) * hp + part);
+            }
         }
         cp_async_commit();
     };
     auto convert = [&](int k) {   // the pieces this thread staged itself: no cross-thread dependency
         if (k < nck) {
-            const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
-            const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
-            double2 d0, d1;
-            d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
-            d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
-            double2* dst = reinterpret_cast<double2*>(&sm.d[k & 1][pj][part]);
-            dst[0] = d0; dst[1] = d1;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int pj = pj0 + 32 * i;
+                const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
+                const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
+                double2 d0, d1;
+                d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
+                d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
+                double2* dst = reinterpret_cast<double2*>(&sm.d[k & 1][pj][part]);
+                dst[0] = d0; dst[1] = d1;
+            }
         }
     };
-    auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3
-        const int r = ht >> 3, c0 = (ht & 7) * 4;
+    auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3 of every 32-column group
+        const int r = ht >> 3;
         const int xbase = k * kRowChunk, n = min(kRowChunk, w - xbase);
         if (r < nrows) {
-            const double* __restrict__ ps = &sm.s[k & 1][r][c0];
-            double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
-            if (c0 + 3 < n) {
-                reinterpret_cast<double2*>(dst)[0] = make_double2(ps[0], ps[1]);
-                reinterpret_cast<double2*>(dst)[1] = make_double2(ps[2], ps[3]);
-            } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (c0 + i < n) dst[i] = ps[i];
+            for (int i = 0; i < NP; ++i) {
+                const int c0 = (ht & 7) * 4 + 32 * i;
+                const double* __restrict__ ps = &sm.s[k & 1][r][c0];
+                double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
+                if (c0 + 3 < n) {
+                    reinterpret_cast<double2*>(dst)[0] = make_double2(ps[0], ps[1]);
+                    reinterpret_cast<double2*>(dst)[1] = make_double2(ps[2], ps[3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c0 + q < n) dst[q] = ps[q];
+                }
             }
         }
     };
