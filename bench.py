@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=0, help="distinct device-resident pairs (0 = enough to exceed L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-detection", action="store_true", help="skip the Shi-Tomasi detection section (SURVEY s8f rank 2)")
     args = ap.parse_args()
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.warmup < 3:
@@ -428,6 +429,60 @@ def main():
         bms = be[0].elapsed_time(be[1])
         batched = {"pairs": P, "points": P * n, "ms": bms, "keypoints_per_sec": P * n / (bms * 1e-3), "pairs_per_sec": P / (bms * 1e-3)}
 
+        # ---- next row of the scope table: Shi-Tomasi detection with the reference's parameters
+        # (src/extractor/extractor.py:21-24), once per frame.  Reported next to the headline, not part of `value`. -----
+        detection = None
+        if not args.no_detection and h > 31 and w > 31:
+            from visual_odom_pipeline_b200 import detector as D
+            det_kw = dict(maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)
+            dimgs = [x[0] for x in hpin]
+            dmask = K.pinned_empty(dimgs[0].shape, np.uint8)
+            dmask[...] = 255
+            for k_ in range(0, 400):   # discs around "tracked" keypoints, as extractor.py:102-107 builds the mask
+                cy, cx = int(hp[0][2].reshape(-1, 2)[k_ % n][1]), int(hp[0][2].reshape(-1, 2)[k_ % n][0])
+                dmask[max(cy - 7, 0):cy + 8, max(cx - 7, 0):cx + 8] = 0
+            for r_ in range(5):
+                got = K.goodFeaturesToTrack(dimgs[r_ % n_host], mask=dmask, device=local_rank, **det_kw)
+            dreps = 200
+            t0 = time.perf_counter()
+            for r_ in range(dreps):
+                K.goodFeaturesToTrack(dimgs[r_ % n_host], mask=dmask, device=local_rank, **det_kw)
+            det_ms = 1e3 * (time.perf_counter() - t0) / dreps
+            # device-resident, batched eigenvalue maps (the kernels only): 64 frames per launch sequence
+            nbd = min(64, 2 * P)
+            de = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for r_ in range(3):
+                if r_ == 2:
+                    de[0].record(stream)
+                eigs = D.corner_min_eigen_val(imgs[:nbd, :, :w], 31)
+            de[1].record(stream)
+            torch.cuda.synchronize()
+            eig_ms = de[0].elapsed_time(de[1])
+            detection = {"api": "visual_odom_pipeline_b200.goodFeaturesToTrack(numpy pinned image, mask, %s) -> numpy" % det_kw,
+                         "e2e_ms_per_frame": det_ms, "frames_per_sec": 1e3 / det_ms, "corners": 0 if got is None else int(len(got)),
+                         "h2d_bytes_per_frame": 2 * w * h,
+                         "batched_min_eig": {"frames": nbd, "ms": eig_ms, "us_per_frame": 1e3 * eig_ms / nbd,
+                                             "mpixels_per_sec": nbd * w * h / (eig_ms * 1e-3) / 1e6,
+                                             "algorithmic_bytes_per_frame": 5 * w * h,
+                                             "note": "u8 frame in, float32 eigenvalue map out; 4 launches per batch (products, running row sums, "
+                                                     "running column sums + eigenvalue, all in OpenCV's summation order)"}}
+            try:
+                import cv2
+                ref = cv2.goodFeaturesToTrack(np.array(dimgs[(dreps - 1) % n_host]), mask=np.array(dmask), **det_kw)
+                detection["parity"] = {"corners_identical_to_cv2": bool((got is None and ref is None) or (got is not None and ref is not None
+                                                                                                      and got.shape == ref.shape and np.array_equal(got, ref)))}
+                if world == 1 and not args.no_cpu_baseline:
+                    ci, cm = np.array(dimgs[0]), np.array(dmask)
+                    for r_ in range(3):
+                        cv2.goodFeaturesToTrack(ci, mask=cm, **det_kw)
+                    t0 = time.perf_counter()
+                    for r_ in range(40):
+                        cv2.goodFeaturesToTrack(ci, mask=cm, **det_kw)
+                    detection["cv2_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / 40
+                    detection["cv2_threads"] = cv2.getNumThreads()
+            except Exception as ex:   # pragma: no cover
+                detection["parity"] = {"error": repr(ex)}
+
         # ---- parity spot check of pool entry used first, against live cv2 ------------------------------------
         parity = None
         try:
@@ -482,6 +537,7 @@ def main():
             "pipelined": pipelined,
             "batched_lk": batched,
             "parity": parity,
+            "detection": detection,
             "cpu_baseline": cpu,
             "device": ctx.name,
         }

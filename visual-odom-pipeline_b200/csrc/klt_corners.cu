@@ -97,6 +97,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// named barriers as producer / consumer signals (PTX bar.arrive / bar.sync pairs): the producer warps arrive after
+// their shared-memory writes, the consumer warps sync before reading; `n` counts the threads of both sides
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // ---- row_scan_kernel ------------------------------------------------------------------------------------------
 // The running sum along x is a serial chain of one DADD per pixel and row, and with so little parallelism (H rows x 3
@@ -104,16 +108,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // nothing but  d = smem, s += d, smem = s;  eight helper warps keep everything else off that warp: they stage the two
 // operand columns of each step (entering and leaving the box; each column of the transposed product image is one
 // 128-byte run over the block's 32 rows) with cp.async kRowStages chunks ahead, form d = (double)new - (double)old
-// exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  One __syncthreads per chunk.
-constexpr int kRowChunk = 64;     // x steps per chunk (multiple of 32)
+// exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  The two sides are coupled only by
+// named-barrier signals over rings of kRowRing chunks (d full / s full / s empty), so the chain warp never waits for a
+// block-wide barrier.
+constexpr int kRowChunk = 32;     // x steps per chunk (multiple of 32)
 constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
+constexpr int kRowRing = 4;       // chunks of d / s between the chain warp and the helpers
+constexpr int kRowLag = 2;        // helpers write out chunk c - kRowLag while the chain works on chunk c (<= kRowRing)
 constexpr int kRowThreads = 32 + 256;
 struct RowSmem {
     float lead[kRowStages][kRowChunk][32];
     float trail[kRowStages][kRowChunk][32];
-    double d[2][kRowChunk][32];
-    double s[2][32][kRowChunk + 1];
+    double d[kRowRing][kRowChunk][32];
+    double s[kRowRing][32][kRowChunk + 1];
 };
+enum { kBarRowDFull = 1, kBarRowSFull = 1 + kRowRing, kBarRowSEmpty = 1 + 2 * kRowRing };
 
 // padded column i (0 <= i < w + block - 1) -> source column (reflect-101 of i - anchor)
 __device__ __forceinline__ int src_col(int i, int an, int w) { return reflect101(i - an, w); }
@@ -144,10 +153,12 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             for (int i = 0; i < 16; ++i)
                 if (i0 + i < block) s = __dadd_rn(s, (double)v[i]);
         }
-        __syncthreads();   // chunk 0 converted
         for (int k = 0; k < nck; ++k) {
-            const double* __restrict__ pd = &sm.d[k & 1][0][lane];
-            double* __restrict__ ps = &sm.s[k & 1][lane][0];
+            const int slot = k % kRowRing;
+            bar_sync(kBarRowDFull + slot, kRowThreads);                       // d[slot] holds chunk k
+            if (k >= kRowRing) bar_sync(kBarRowSEmpty + slot, kRowThreads);   // chunk k - kRowRing has been written out
+            const double* __restrict__ pd = &sm.d[slot][0][lane];
+            double* __restrict__ ps = &sm.s[slot][lane][0];
             // all operands into registers first: the loads must not queue behind the (possibly aliasing) stores
             double v[kRowChunk];
 #pragma unroll
@@ -157,7 +168,7 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             for (int j = 0; j < kRowChunk; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
 #pragma unroll
             for (int j = 0; j < kRowChunk; ++j) ps[j] = v[j];
-            __syncthreads();
+            bar_arrive(kBarRowSFull + slot, kRowThreads);
         }
         return;
     }
@@ -178,28 +189,27 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
         cp_async_commit();
     };
     auto convert = [&](int k) {   // the pieces this thread staged itself: no cross-thread dependency
-        if (k < nck) {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int pj = pj0 + 32 * i;
-                const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
-                const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
-                double2 d0, d1;
-                d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
-                d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
-                double2* dst = reinterpret_cast<double2*>(&sm.d[k & 1][pj][part]);
-                dst[0] = d0; dst[1] = d1;
-            }
+        for (int i = 0; i < NP; ++i) {
+            const int pj = pj0 + 32 * i;
+            const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
+            const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
+            double2 d0, d1;
+            d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
+            d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
+            double2* dst = reinterpret_cast<double2*>(&sm.d[k % kRowRing][pj][part]);
+            dst[0] = d0; dst[1] = d1;
         }
     };
     auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3 of every 32-column group
         const int r = ht >> 3;
         const int xbase = k * kRowChunk, n = min(kRowChunk, w - xbase);
+        bar_sync(kBarRowSFull + k % kRowRing, kRowThreads);
         if (r < nrows) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 const int c0 = (ht & 7) * 4 + 32 * i;
-                const double* __restrict__ ps = &sm.s[k & 1][r][c0];
+                const double* __restrict__ ps = &sm.s[k % kRowRing][r][c0];
                 double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
                 if (c0 + 3 < n) {
                     reinterpret_cast<double2*>(dst)[0] = make_double2(ps[0], ps[1]);
@@ -211,20 +221,19 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
                 }
             }
         }
+        if (k + kRowRing < nck) bar_arrive(kBarRowSEmpty + k % kRowRing, kRowThreads);   // the slot may be rewritten
     };
+    static_assert(kRowLag <= kRowRing, "d[slot] is rewritten only after the chain finished the chunk that was in it");
 #pragma unroll
     for (int k = 0; k < kRowStages; ++k) issue(k);
-    cp_async_wait<kRowStages - 1>();
-    convert(0);
-    __syncthreads();
     for (int k = 0; k < nck; ++k) {
-        if (k >= 1) flush(k - 1);
-        cp_async_wait<kRowStages - 2>();   // chunk k + 1 has landed
-        convert(k + 1);
-        issue(k + kRowStages);             // its slot (chunk k's) was consumed by this thread one iteration ago
-        __syncthreads();
+        if (k >= kRowLag) flush(k - kRowLag);
+        cp_async_wait<kRowStages - 1>();     // chunk k has landed (this thread's pieces)
+        convert(k);
+        bar_arrive(kBarRowDFull + k % kRowRing, kRowThreads);
+        issue(k + kRowStages);               // into the staging slot just consumed
     }
-    flush(nck - 1);
+    for (int k = max(nck - kRowLag, 0); k < nck; ++k) flush(k);
 }
 
 // OpenCV's RowSum forms fresh left-to-right sums for kernel sizes 3 and 5: no chain, one thread per output.
@@ -243,16 +252,19 @@ row_sum_small_kernel(const float* __restrict__ covT, int w, int h, int hp, int b
 
 // ---- col_scan_kernel ------------------------------------------------------------------------------------------
 // Same specialisation along y: warps 0..2 are the chains of the three channels (lane = column; two dependent DADDs
-// per pixel:  t = SUM + entering row,  SUM = t - leaving row), thirteen helper warps stage the entering / leaving
+// per pixel:  t = SUM + entering row,  SUM = t - leaving row), twelve helper warps stage the entering / leaving
 // row-sum rows with cp.async kColStages-1 chunks ahead and turn the finished box sums of the previous chunk into the
-// eigenvalue (G.6), the masked maximum and the coalesced float32 output.
+// eigenvalue (G.6), the masked maximum and the coalesced float32 output.  Coupling by named-barrier signals only
+// (stage full / t full / t empty).
 constexpr int kColChunk = 16;     // y steps per chunk
-constexpr int kColStages = 4;
+constexpr int kColStages = 6;     // stages of operand rows (ring between the loaders and the chains)
+constexpr int kColRing = 4;       // chunks of box sums between the chains and the helpers
 constexpr int kColThreads = 96 + 384, kColHelpers = kColThreads - 96;
 struct ColSmem {
     double st[kColStages][2][3][kColChunk][32];   // [stage][entering / leaving][channel][row][column]
-    float t[2][3][kColChunk][32];
+    float t[kColRing][3][kColChunk][32];
 };
+enum { kBarColStFull = 1, kBarColTFull = 1 + kColStages, kBarColTEmpty = 1 + kColStages + kColRing };
 
 __global__ void __launch_bounds__(kColThreads)
 col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block, float* __restrict__ eig, long long eig_pitch,
@@ -280,11 +292,12 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
             for (int i = 0; i < 16; ++i)
                 if (i0 + i < block - 1) s = __dadd_rn(s, v[i]);
         }
-        __syncthreads();   // chunk 0 staged
         for (int k = 0; k < nck; ++k) {
+            bar_sync(kBarColStFull + k % kColStages, kColThreads);                        // operand rows of chunk k staged
+            if (k >= kColRing) bar_sync(kBarColTEmpty + k % kColRing, kColThreads);       // chunk k - kColRing turned into eigenvalues
             const double* __restrict__ pe = &sm.st[k % kColStages][0][wrp][0][lane];
             const double* __restrict__ pl = &sm.st[k % kColStages][1][wrp][0][lane];
-            float* __restrict__ pt = &sm.t[k & 1][wrp][0][lane];
+            float* __restrict__ pt = &sm.t[k % kColRing][wrp][0][lane];
             double ve[kColChunk], vl[kColChunk];   // operands into registers first (see row_scan_kernel)
 #pragma unroll
             for (int j = 0; j < kColChunk; ++j) { ve[j] = pe[j * 32]; vl[j] = pl[j * 32]; }
@@ -295,7 +308,7 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
             }
 #pragma unroll
             for (int j = 0; j < kColChunk; ++j) pt[j * 32] = __double2float_rn(ve[j]);
-            __syncthreads();
+            bar_arrive(kBarColTFull + k % kColRing, kColThreads);   // also: this chain is done with the stage
         }
         return;
     }
@@ -333,7 +346,7 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
     };
     auto finish_px = [&](int k, int j, unsigned m) {
         const int y = k * kColChunk + j, x = x0 + fx;
-        const float a = __fmul_rn(sm.t[k & 1][0][j][fx], 0.5f), b = sm.t[k & 1][1][j][fx], c = __fmul_rn(sm.t[k & 1][2][j][fx], 0.5f);
+        const float a = __fmul_rn(sm.t[k % kColRing][0][j][fx], 0.5f), b = sm.t[k % kColRing][1][j][fx], c = __fmul_rn(sm.t[k % kColRing][2][j][fx], 0.5f);
         const float d = __fsub_rn(a, c);
         const float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));   // G.6
         if (x < w && y < h) {
@@ -341,22 +354,24 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
             if (max_out && m) best = max(best, ordered_from_float(e));
         }
     };
-    auto finish = [&](int k, unsigned m0, unsigned m1) {  // eigenvalues of chunk k
+    auto finish = [&](int k, unsigned m0, unsigned m1) {  // eigenvalues of chunk k, once all three chains have delivered it
+        bar_sync(kBarColTFull + k % kColRing, kColThreads);
         finish_px(k, fj0, m0);
         if (fj0 + kColHelpers / 32 < kColChunk) finish_px(k, fj0 + kColHelpers / 32, m1);
+        if (k + kColRing < nck) bar_arrive(kBarColTEmpty + k % kColRing, kColThreads);
     };
 #pragma unroll
     for (int k = 0; k < kColStages - 1; ++k) issue(k);
     cp_async_wait<kColStages - 2>();
-    __syncthreads();
+    bar_arrive(kBarColStFull + 0, kColThreads);                  // chunk 0 staged (nck >= 1)
     unsigned mc0 = 1u, mc1 = 1u;
     for (int k = 0; k < nck; ++k) {
-        issue(k + kColStages - 1);          // into the slot of chunk k - 1, consumed before the last barrier
         unsigned mn0, mn1;
-        load_mask(k, mn0, mn1);             // consumed one iteration later: the load latency hides behind the barrier
-        if (k >= 1) finish(k - 1, mc0, mc1);
-        cp_async_wait<kColStages - 2>();    // chunk k + 1 has landed
-        __syncthreads();
+        load_mask(k, mn0, mn1);             // consumed one iteration later: the load latency hides behind the waits
+        if (k >= 1) finish(k - 1, mc0, mc1);   // implies: the chains are done with the stage of chunk k - 1 ...
+        issue(k + kColStages - 1);             // ... which is the stage this refills
+        cp_async_wait<kColStages - 2>();       // chunk k + 1 has landed (this thread's pieces)
+        if (k + 1 < nck) bar_arrive(kBarColStFull + (k + 1) % kColStages, kColThreads);
         mc0 = mn0; mc1 = mn1;
     }
     finish(nck - 1, mc0, mc1);
