@@ -468,7 +468,8 @@ def main():
                                                      "running column sums + eigenvalue, all in OpenCV's summation order)"}}
             try:
                 import cv2
-                ref = cv2.goodFeaturesToTrack(np.array(dimgs[(dreps - 1) % n_host]), mask=np.array(dmask), **det_kw)
+                got = K.goodFeaturesToTrack(dimgs[0], mask=dmask, device=local_rank, **det_kw)
+                ref = cv2.goodFeaturesToTrack(np.array(dimgs[0]), mask=np.array(dmask), **det_kw)
                 detection["parity"] = {"corners_identical_to_cv2": bool((got is None and ref is None) or (got is not None and ref is not None
                                                                                                       and got.shape == ref.shape and np.array_equal(got, ref)))}
                 if world == 1 and not args.no_cpu_baseline:

@@ -19,4 +19,11 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:pyr_
     python scripts/prof_target.py pyr > $OUT/prof_pyr.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_fast -s 1 -c 2 -o $OUT/prof_lk -f \
     python scripts/prof_target.py lk > $OUT/prof_lk.log 2>&1
+# detection step: launch list of goodFeaturesToTrack calls, full capture of the two running-sum kernels
+timeout 300 python scripts/corners_time.py > $OUT/corners_time.log 2>&1
+KLT_TRACE=1 REPS=5 timeout 300 python scripts/corners_time.py >> $OUT/corners_time.log 2>&1
+REPS=5 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/corners_launches.csv \
+    python scripts/corners_time.py > /dev/null 2>&1
+REPS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 2 -c 2 -o $OUT/prof_corners -f \
+    python scripts/corners_time.py > $OUT/prof_corners.log 2>&1
 ls -la $OUT

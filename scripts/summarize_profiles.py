@@ -20,7 +20,8 @@ for f in os.listdir(src):
 
 def short(name):
     for key in ("lk_fast_kernel", "lk_kernel", "pyr_down_ring_kernel", "pyr_down_tma_kernel", "pyr_down_kernel", "repitch_kernel",
-                "track_filter_kernel", "min_eig", "corner"):
+                "track_filter_kernel", "cov_kernel", "row_scan_kernel", "row_sum_small_kernel", "col_scan_kernel", "candidates_kernel",
+                "rank_keys_kernel", "scatter_keys_kernel"):
         if key in name:
             tail = name.split(key, 1)[1]
             targs = tail.split("(", 1)[0]
@@ -56,6 +57,32 @@ if os.path.exists(launches):
         f.write("\nfirst 40 launches in order:\n")
         for k, g, b, us in rows[:40]:
             f.write("  %-60s %-14s %-12s %9.2f us\n" % (k, g, b, us))
+
+corners = os.path.join(src, "corners_launches.csv")
+if os.path.exists(corners):
+    with open(corners) as f:
+        text = f.read()
+    start = text.find('"ID"')
+    rows = []
+    for r in csv.DictReader(io.StringIO(text[start:])):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            v = float(r["Metric Value"].replace(",", ""))
+            unit = r["Metric Unit"]
+            us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+            rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], us))
+    agg = collections.OrderedDict()
+    for k, g, b, us in rows:
+        a = agg.setdefault(k, [0, 0.0, g, b])
+        a[0] += 1
+        a[1] += us
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(dst, "corners_launches_summary.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none over `python scripts/corners_time.py` (goodFeaturesToTrack on a\n")
+        f.write("KITTI-shape frame with the reference's parameters; per-launch times are cold-cache and serialised -> shares only)\n")
+        f.write("%d launches captured, %.1f us total\n\n" % (len(rows), tot))
+        f.write("%-40s %8s %12s %10s %7s  %s\n" % ("kernel", "launches", "total us", "avg us", "share", "grid x block (first)"))
+        for k, (n, us, g, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-40s %8d %12.1f %10.2f %6.1f%%  %s x %s\n" % (k, n, us, us / n, 100 * us / tot, g, b))
 
 for rep in sorted(os.listdir(src)):
     if rep.endswith(".ncu-rep"):

@@ -105,17 +105,18 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 // ---- row_scan_kernel ------------------------------------------------------------------------------------------
 // The running sum along x is a serial chain of one DADD per pixel and row, and with so little parallelism (H rows x 3
 // channels) the launch time IS the time of one chain.  So the block is specialised: warp 0 ("chain", lane = row) does
-// nothing but  d = smem, s += d, smem = s;  eight helper warps keep everything else off that warp: they stage the two
+// nothing but  d = smem, s += d, smem = s;  sixteen helper warps keep everything else off that warp: they stage the two
 // operand columns of each step (entering and leaving the box; each column of the transposed product image is one
 // 128-byte run over the block's 32 rows) with cp.async kRowStages chunks ahead, form d = (double)new - (double)old
 // exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  The two sides are coupled only by
 // named-barrier signals over rings of kRowRing chunks (d full / s full / s empty), so the chain warp never waits for a
 // block-wide barrier.
-constexpr int kRowChunk = 32;     // x steps per chunk (multiple of 32)
+constexpr int kRowChunk = 64;     // x steps per chunk (multiple of 32)
 constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
 constexpr int kRowRing = 4;       // chunks of d / s between the chain warp and the helpers
 constexpr int kRowLag = 2;        // helpers write out chunk c - kRowLag while the chain works on chunk c (<= kRowRing)
-constexpr int kRowThreads = 32 + 256;
+constexpr int kRowHelpers = 512;  // helper threads: the per-chunk latency of a helper is what bounds the chain, so many warps with little work each
+constexpr int kRowThreads = 32 + kRowHelpers;
 struct RowSmem {
     float lead[kRowStages][kRowChunk][32];
     float trail[kRowStages][kRowChunk][32];
@@ -157,17 +158,20 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             const int slot = k % kRowRing;
             bar_sync(kBarRowDFull + slot, kRowThreads);                       // d[slot] holds chunk k
             if (k >= kRowRing) bar_sync(kBarRowSEmpty + slot, kRowThreads);   // chunk k - kRowRing has been written out
-            const double* __restrict__ pd = &sm.d[slot][0][lane];
-            double* __restrict__ ps = &sm.s[slot][lane][0];
-            // all operands into registers first: the loads must not queue behind the (possibly aliasing) stores
-            double v[kRowChunk];
 #pragma unroll
-            for (int j = 0; j < kRowChunk; ++j) v[j] = pd[j * 32];
-            if (k == 0) v[0] = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
+            for (int hh = 0; hh < kRowChunk / 32; ++hh) {
+                const double* __restrict__ pd = &sm.d[slot][32 * hh][lane];
+                double* __restrict__ ps = &sm.s[slot][lane][32 * hh];
+                // all operands into registers first: the loads must not queue behind the (possibly aliasing) stores
+                double v[32];
 #pragma unroll
-            for (int j = 0; j < kRowChunk; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
+                for (int j = 0; j < 32; ++j) v[j] = pd[j * 32];
+                if (k == 0 && hh == 0) v[0] = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
 #pragma unroll
-            for (int j = 0; j < kRowChunk; ++j) ps[j] = v[j];
+                for (int j = 0; j < 32; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ps[j] = v[j];
+            }
             bar_arrive(kBarRowSFull + slot, kRowThreads);
         }
         return;
@@ -175,12 +179,14 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
     // ---- helper warps: thread = 16-byte pieces (4 rows) of kRowChunk / 32 staged columns ----
     const int ht = tid - 32;
     const int pj0 = ht >> 3, part = (ht & 7) * 4;   // first column within the chunk, first of 4 rows
-    constexpr int NP = kRowChunk / 32;
+    constexpr int PJ = kRowHelpers / 8;             // columns staged per pass over the helper threads
+    constexpr int NP = kRowChunk / PJ;
+    static_assert(kRowChunk % PJ == 0 && kRowHelpers % 256 == 0, "helper thread mapping");
     auto issue = [&](int k) {
         if (k < nck) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
-                const int pj = pj0 + 32 * i;
+                const int pj = pj0 + PJ * i;
                 const int o = min(max(k * kRowChunk + pj, 1), w - 1 > 1 ? w - 1 : 1);
                 cp_async16(&sm.lead[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1 + block, an, w) * hp + part);
                 cp_async16(&sm.trail[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1, an, w) * hp + part);
@@ -191,7 +197,7 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
     auto convert = [&](int k) {   // the pieces this thread staged itself: no cross-thread dependency
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            const int pj = pj0 + 32 * i;
+            const int pj = pj0 + PJ * i;
             const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
             const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
             double2 d0, d1;
@@ -202,13 +208,13 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
         }
     };
     auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3 of every 32-column group
-        const int r = ht >> 3;
+        const int r = (ht >> 3) & 31;
         const int xbase = k * kRowChunk, n = min(kRowChunk, w - xbase);
         bar_sync(kBarRowSFull + k % kRowRing, kRowThreads);
         if (r < nrows) {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int c0 = (ht & 7) * 4 + 32 * i;
+            for (int i = 0; i < kRowChunk / (kRowHelpers / 8); ++i) {
+                const int c0 = (ht & 7) * 4 + 32 * (ht >> 8) + (kRowHelpers / 8) * i;
                 const double* __restrict__ ps = &sm.s[k % kRowRing][r][c0];
                 double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
                 if (c0 + 3 < n) {
@@ -223,15 +229,16 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
         }
         if (k + kRowRing < nck) bar_arrive(kBarRowSEmpty + k % kRowRing, kRowThreads);   // the slot may be rewritten
     };
-    static_assert(kRowLag <= kRowRing, "d[slot] is rewritten only after the chain finished the chunk that was in it");
+    static_assert(kRowLag + 1 <= kRowRing, "d[slot] is rewritten only after the chain finished the chunk that was in it");
 #pragma unroll
     for (int k = 0; k < kRowStages; ++k) issue(k);
     for (int k = 0; k < nck; ++k) {
-        if (k >= kRowLag) flush(k - kRowLag);
+        // feed the chain first: d[k % ring] is free because this thread has already seen "s full" of chunk k - 1 - lag
         cp_async_wait<kRowStages - 1>();     // chunk k has landed (this thread's pieces)
         convert(k);
         bar_arrive(kBarRowDFull + k % kRowRing, kRowThreads);
         issue(k + kRowStages);               // into the staging slot just consumed
+        if (k >= kRowLag) flush(k - kRowLag);
     }
     for (int k = max(nck - kRowLag, 0); k < nck; ++k) flush(k);
 }
@@ -252,14 +259,14 @@ row_sum_small_kernel(const float* __restrict__ covT, int w, int h, int hp, int b
 
 // ---- col_scan_kernel ------------------------------------------------------------------------------------------
 // Same specialisation along y: warps 0..2 are the chains of the three channels (lane = column; two dependent DADDs
-// per pixel:  t = SUM + entering row,  SUM = t - leaving row), twelve helper warps stage the entering / leaving
+// per pixel:  t = SUM + entering row,  SUM = t - leaving row), twenty-four helper warps stage the entering / leaving
 // row-sum rows with cp.async kColStages-1 chunks ahead and turn the finished box sums of the previous chunk into the
 // eigenvalue (G.6), the masked maximum and the coalesced float32 output.  Coupling by named-barrier signals only
 // (stage full / t full / t empty).
 constexpr int kColChunk = 16;     // y steps per chunk
 constexpr int kColStages = 6;     // stages of operand rows (ring between the loaders and the chains)
 constexpr int kColRing = 4;       // chunks of box sums between the chains and the helpers
-constexpr int kColThreads = 96 + 384, kColHelpers = kColThreads - 96;
+constexpr int kColThreads = 96 + 768, kColHelpers = kColThreads - 96;
 struct ColSmem {
     double st[kColStages][2][3][kColChunk][32];   // [stage][entering / leaving][channel][row][column]
     float t[kColRing][3][kColChunk][32];
@@ -316,17 +323,18 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
     const int ht = tid - 96;
     float* __restrict__ E = eig + (long long)blockIdx.z * eig_batch_stride;
     const uint8_t* __restrict__ M = mask ? mask + (long long)blockIdx.z * mask_batch_stride : nullptr;
-    static_assert(2 * 3 * kColChunk * 16 == 4 * kColHelpers, "4 pieces per helper thread");
+    constexpr int NRG = kColHelpers / 96;               // row groups: 16 pieces x 6 planes per row
+    static_assert(kColHelpers % 96 == 0 && kColChunk % NRG == 0, "whole rows per helper thread");
     const int part2 = (ht & 15) * 2;                   // piece = 2 doubles of a 32-column row
-    const int pp = (ht >> 4) % 6, prg = (ht >> 4) / 6;  // plane (entering / leaving x channel), row group 0..3
+    const int pp = (ht >> 4) % 6, prg = (ht >> 4) / 6;  // plane (entering / leaving x channel), row group 0..NRG-1
     const int plt = pp / 3, pc = pp - 3 * plt;
     const double* __restrict__ Rp = R + pc * plane + part2;
     auto issue = [&](int k) {   // rows entering (y + block - 1 - an) and leaving (y - an) for y in chunk k
         if (k < nck) {
             double* st = &sm.st[k % kColStages][plt][pc][0][part2];
 #pragma unroll
-            for (int i = 0; i < kColChunk / 4; ++i) {
-                const int r = prg + 4 * i;
+            for (int i = 0; i < kColChunk / NRG; ++i) {
+                const int r = prg + NRG * i;
                 const int y = min(k * kColChunk + r, h - 1);
                 const int sy = reflect101(plt ? y - an : y + block - 1 - an, h);
                 cp_async16(st + r * 32, Rp + (long long)sy * wd);
@@ -338,9 +346,9 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
     const int fj0 = ht >> 5, fx = ht & 31;   // pixels (row fj0, column fx) and (row fj0 + kColHelpers / 32, column fx) of a chunk
     auto load_mask = [&](int k, unsigned& m0, unsigned& m1) {
         m0 = 1u; m1 = 1u;
-        if (M && k < nck) {
+        if (M && k >= 0 && k < nck) {
             const int x = x0 + fx, ya = k * kColChunk + fj0, yb = ya + kColHelpers / 32;
-            if (x < w && ya < h) m0 = M[(long long)ya * mask_pitch + x];
+            if (x < w && ya < h && fj0 < kColChunk) m0 = M[(long long)ya * mask_pitch + x];
             if (x < w && yb < h && fj0 + kColHelpers / 32 < kColChunk) m1 = M[(long long)yb * mask_pitch + x];
         }
     };
@@ -356,23 +364,28 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
     };
     auto finish = [&](int k, unsigned m0, unsigned m1) {  // eigenvalues of chunk k, once all three chains have delivered it
         bar_sync(kBarColTFull + k % kColRing, kColThreads);
-        finish_px(k, fj0, m0);
+        if (fj0 < kColChunk) finish_px(k, fj0, m0);
         if (fj0 + kColHelpers / 32 < kColChunk) finish_px(k, fj0 + kColHelpers / 32, m1);
         if (k + kColRing < nck) bar_arrive(kBarColTEmpty + k % kColRing, kColThreads);
     };
 #pragma unroll
-    for (int k = 0; k < kColStages - 1; ++k) issue(k);
-    cp_async_wait<kColStages - 2>();
-    bar_arrive(kBarColStFull + 0, kColThreads);                  // chunk 0 staged (nck >= 1)
+    for (int k = 0; k < kColStages - 2; ++k) issue(k);
     unsigned mc0 = 1u, mc1 = 1u;
     for (int k = 0; k < nck; ++k) {
+        // feed the chains first, then finish chunk k - 2 (two chunks of slack before they could starve)
+        cp_async_wait<kColStages - 3>();       // chunk k has landed (this thread's pieces)
+        bar_arrive(kBarColStFull + k % kColStages, kColThreads);
         unsigned mn0, mn1;
-        load_mask(k, mn0, mn1);             // consumed one iteration later: the load latency hides behind the waits
-        if (k >= 1) finish(k - 1, mc0, mc1);   // implies: the chains are done with the stage of chunk k - 1 ...
-        issue(k + kColStages - 1);             // ... which is the stage this refills
-        cp_async_wait<kColStages - 2>();       // chunk k + 1 has landed (this thread's pieces)
-        if (k + 1 < nck) bar_arrive(kBarColStFull + (k + 1) % kColStages, kColThreads);
+        load_mask(k - 1, mn0, mn1);            // consumed one iteration later: the load latency hides behind the waits
+        if (k >= 2) finish(k - 2, mc0, mc1);   // implies: the chains are done with the stage of chunk k - 2 ...
+        issue(k + kColStages - 2);             // ... which is the stage this refills
         mc0 = mn0; mc1 = mn1;
+    }
+    if (nck >= 2) {
+        finish(nck - 2, mc0, mc1);
+        load_mask(nck - 1, mc0, mc1);
+    } else {
+        load_mask(0, mc0, mc1);
     }
     finish(nck - 1, mc0, mc1);
     if (max_out) {
