@@ -1,0 +1,21 @@
+"""Chain-warp timeline of row_scan_kernel (profiling aid): where one chunk's cycles go."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import visual_odom_pipeline_b200 as K
+from visual_odom_pipeline_b200 import _lib, synth as S
+L = _lib.load()
+L.klt_debug_corner_timeline.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+a = S.frame_pair(376, 1241, seed=3)[0]
+for _ in range(3): K.cornerMinEigenVal(a, 31)
+assert L.klt_debug_corner_timeline(1, None, 0) == 0
+K.cornerMinEigenVal(a, 31)
+buf = np.zeros(1024, np.int64)
+assert L.klt_debug_corner_timeline(0, buf.ctypes.data, 1024) == 0
+t = buf.reshape(-1, 4)
+n = int((t[:, 0] != 0).sum())
+t = t[:n] - t[0, 0]
+print("chunk: start, wait d-full, wait s-empty, compute+arrive (cycles)")
+for k in range(n):
+    print("%3d: %7d  %6d %6d %6d" % (k, t[k, 0], t[k, 1] - t[k, 0], t[k, 2] - t[k, 1], t[k, 3] - t[k, 2]))
+print("total", t[n - 1, 3], "cycles for", n, "chunks")

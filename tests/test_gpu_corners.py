@@ -133,3 +133,53 @@ def test_batched_device_api_equals_per_frame_host_calls(klt, cv2):
     for b in range(B):
         assert_eig_equal(eig[b].cpu().numpy(), cv2.cornerMinEigenVal(frames[b], 31, ksize=3))
         assert same(res[b], cv2.goodFeaturesToTrack(frames[b], 500, 0.03, 10, mask=masks[b], blockSize=31)), "frame %d" % b
+
+
+def _frame_loop(lk, gftt, cv2, frames, n_init):
+    """The data-parallel part of the reference's per-frame step (src/pipeline/pipeline.py:92-103,159-163 with
+    src/extractor/extractor.py:38-59, 61-88, 95-112): track candidate and landmark keypoints with two LK calls each, drop
+    points by bidirectional error and the inclusive bounds test, mask discs around the survivors, detect new candidates."""
+    lk_params = dict(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))                    # extractor.py:16-19
+    st_params = dict(maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)        # extractor.py:21-24
+    h, w = frames[0].shape
+    first = gftt(frames[0], mask=None, **st_params).reshape(-1, 2)
+    landmarks, candidates = first[:n_init], first[n_init:]
+    trace = []
+    for t in range(1, len(frames)):
+        im0, im1 = frames[t - 1], frames[t]
+        groups = []
+        for p0 in (candidates, landmarks):
+            if len(p0) == 0:
+                groups.append(p0)
+                continue
+            p0 = np.float32(p0).reshape(-1, 1, 2)
+            p1, _st, _err = lk(im0, im1, p0, None, **lk_params)
+            p0r, _st, _err = lk(im0, im1, p1, None, **lk_params)
+            d = abs(p0 - p0r).reshape(-1, 2).max(-1)
+            good = d < 30
+            p1 = p1.reshape(-1, 2)
+            keep = good & (0 <= p1[:, 0]) & (p1[:, 0] <= w) & (0 <= p1[:, 1]) & (p1[:, 1] <= h)
+            groups.append(p1[keep])
+        candidates, landmarks = groups
+        mask = np.zeros_like(im1)
+        mask[:] = 255
+        for x, y in [np.int32(p) for p in np.concatenate([landmarks, candidates])]:
+            cv2.circle(mask, (int(x), int(y)), 10, 0, -1)
+        new = gftt(im1.copy(), mask=mask, **st_params)
+        if new is not None:
+            candidates = np.concatenate([candidates, new.reshape(-1, 2)])
+        trace.append((landmarks.copy(), candidates.copy()))
+    return trace
+
+
+def test_reference_frame_loop_malaga_shape(klt, cv2):
+    """BASELINE configs[2] shape (1024 x 768, ~3000 keypoints tracked frame to frame): the tracking + detection calls of
+    the reference's step, chained over a sequence, give identical keypoint sets with this library and with cv2."""
+    frames = S.sequence(768, 1024, 6, seed=12)
+    got = _frame_loop(klt.calcOpticalFlowPyrLK, klt.goodFeaturesToTrack, cv2, frames, 600)
+    want = _frame_loop(cv2.calcOpticalFlowPyrLK, cv2.goodFeaturesToTrack, cv2, frames, 600)
+    assert len(got) == len(want) == 5
+    for t, ((l1, c1), (l2, c2)) in enumerate(zip(got, want)):
+        assert l1.shape == l2.shape and np.array_equal(l1.view(np.uint32), l2.view(np.uint32)), "landmarks differ at frame %d" % (t + 1)
+        assert c1.shape == c2.shape and np.array_equal(c1.view(np.uint32), c2.view(np.uint32)), "candidates differ at frame %d" % (t + 1)
+    assert len(got[-1][0]) + len(got[-1][1]) > 2000

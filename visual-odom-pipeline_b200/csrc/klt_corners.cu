@@ -102,6 +102,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// profiling aid (KLT_CORNER_TIMELINE=1, scripts/corner_timeline.py): clock64 stamps of the chain warp of block (0,0,0)
+__device__ long long g_timeline[4 * 256];
+__device__ int g_timeline_on;
+
 // ---- row_scan_kernel ------------------------------------------------------------------------------------------
 // The running sum along x is a serial chain of one DADD per pixel and row, and with so little parallelism (H rows x 3
 // channels) the launch time IS the time of one chain.  So the block is specialised: warp 0 ("chain", lane = row) does
@@ -116,19 +120,22 @@ constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
 constexpr int kRowRing = 4;       // chunks of d / s between the chain warp and the helpers
 constexpr int kRowLag = 2;        // helpers write out chunk c - kRowLag while the chain works on chunk c (<= kRowRing)
 constexpr int kRowHelpers = 512;  // helper threads: the per-chunk latency of a helper is what bounds the chain, so many warps with little work each
-constexpr int kRowThreads = 32 + kRowHelpers;
+constexpr int kRowThreads = 32 + kRowHelpers;            // threads that take part in the named barriers
+constexpr int kRowBlock = 32 * (1 + kRowHelpers / 32 + (kRowHelpers / 32 + 2) / 3);   // + idle warps, see below
 struct RowSmem {
     float lead[kRowStages][kRowChunk][32];
     float trail[kRowStages][kRowChunk][32];
-    double d[kRowRing][kRowChunk][32];
-    double s[kRowRing][32][kRowChunk + 1];
+    // lane-major with a row stride of kRowChunk + 2 doubles (16-byte aligned, an odd number of 16-byte units): the chain
+    // warp moves two steps per 128-bit shared-memory access, conflict-free
+    double d[kRowRing][32][kRowChunk + 2];
+    double s[kRowRing][32][kRowChunk + 2];
 };
 enum { kBarRowDFull = 1, kBarRowSFull = 1 + kRowRing, kBarRowSEmpty = 1 + 2 * kRowRing };
 
 // padded column i (0 <= i < w + block - 1) -> source column (reflect-101 of i - anchor)
 __device__ __forceinline__ int src_col(int i, int an, int w) { return reflect101(i - an, w); }
 
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowBlock)
 row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block, double* __restrict__ rows, int wd)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -154,30 +161,52 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             for (int i = 0; i < 16; ++i)
                 if (i0 + i < block) s = __dadd_rn(s, (double)v[i]);
         }
+        const bool tl_on = g_timeline_on && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
         for (int k = 0; k < nck; ++k) {
             const int slot = k % kRowRing;
+            const bool tl = tl_on && k < 256;
+            if (tl) g_timeline[4 * k] = clock64();
             bar_sync(kBarRowDFull + slot, kRowThreads);                       // d[slot] holds chunk k
+            if (tl) g_timeline[4 * k + 1] = clock64();
             if (k >= kRowRing) bar_sync(kBarRowSEmpty + slot, kRowThreads);   // chunk k - kRowRing has been written out
+            if (tl) g_timeline[4 * k + 2] = clock64();
+            // 16 steps at a time, the next 16 operands already requested (two register buffers).  Measured (timeline of
+            // scripts/corner_timeline.py): ~22 cycles per step although a dependent DADD takes 8 -- ptxas interleaves the
+            // loads and stores with the chain and gives a load the registers a store has just read, and the in-order issue
+            // of the DADDs waits for that store; fences (one-warp named barriers) around the chain made it worse.
+            const double2* __restrict__ pd = reinterpret_cast<const double2*>(&sm.d[slot][lane][0]);
+            double2* __restrict__ ps = reinterpret_cast<double2*>(&sm.s[slot][lane][0]);
+            double2 buf[2][8];
 #pragma unroll
-            for (int hh = 0; hh < kRowChunk / 32; ++hh) {
-                const double* __restrict__ pd = &sm.d[slot][32 * hh][lane];
-                double* __restrict__ ps = &sm.s[slot][lane][32 * hh];
-                // all operands into registers first: the loads must not queue behind the (possibly aliasing) stores
-                double v[32];
+            for (int j = 0; j < 8; ++j) buf[0][j] = pd[j];
+            if (k == 0) buf[0][0].x = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = pd[j * 32];
-                if (k == 0 && hh == 0) v[0] = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
+            for (int q = 0; q < kRowChunk / 16; ++q) {
+                if (q + 1 < kRowChunk / 16) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
+                    for (int j = 0; j < 8; ++j) buf[(q + 1) & 1][j] = pd[8 * (q + 1) + j];
+                }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ps[j] = v[j];
+                for (int j = 0; j < 8; ++j) {
+                    s = __dadd_rn(s, buf[q & 1][j].x); buf[q & 1][j].x = s;
+                    s = __dadd_rn(s, buf[q & 1][j].y); buf[q & 1][j].y = s;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ps[8 * q + j] = buf[q & 1][j];
             }
             bar_arrive(kBarRowSFull + slot, kRowThreads);
+            if (tl) g_timeline[4 * k + 3] = clock64();
         }
         return;
     }
+    // The chain warp gets a warp scheduler to itself: warps are dealt to the four schedulers round-robin, so every
+    // other warp whose index is a multiple of 4 is left idle (timeline: the chain no longer waits for its operands, 250-650
+    // cycles per chunk before).
+    const int wrp = tid >> 5;
+    if ((wrp & 3) == 0) return;
     // ---- helper warps: thread = 16-byte pieces (4 rows) of kRowChunk / 32 staged columns ----
-    const int ht = tid - 32;
+    const int ht = (wrp - 1 - (wrp >> 2)) * 32 + lane;
+    if (ht >= kRowHelpers) return;
     const int pj0 = ht >> 3, part = (ht & 7) * 4;   // first column within the chunk, first of 4 rows
     constexpr int PJ = kRowHelpers / 8;             // columns staged per pass over the helper threads
     constexpr int NP = kRowChunk / PJ;
@@ -200,11 +229,11 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             const int pj = pj0 + PJ * i;
             const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
             const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
-            double2 d0, d1;
-            d0.x = __dsub_rn((double)a.x, (double)b.x); d0.y = __dsub_rn((double)a.y, (double)b.y);
-            d1.x = __dsub_rn((double)a.z, (double)b.z); d1.y = __dsub_rn((double)a.w, (double)b.w);
-            double2* dst = reinterpret_cast<double2*>(&sm.d[k % kRowRing][pj][part]);
-            dst[0] = d0; dst[1] = d1;
+            double (*dst)[kRowChunk + 2] = sm.d[k % kRowRing];
+            dst[part + 0][pj] = __dsub_rn((double)a.x, (double)b.x);
+            dst[part + 1][pj] = __dsub_rn((double)a.y, (double)b.y);
+            dst[part + 2][pj] = __dsub_rn((double)a.z, (double)b.z);
+            dst[part + 3][pj] = __dsub_rn((double)a.w, (double)b.w);
         }
     };
     auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3 of every 32-column group
@@ -218,8 +247,9 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
                 const double* __restrict__ ps = &sm.s[k % kRowRing][r][c0];
                 double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
                 if (c0 + 3 < n) {
-                    reinterpret_cast<double2*>(dst)[0] = make_double2(ps[0], ps[1]);
-                    reinterpret_cast<double2*>(dst)[1] = make_double2(ps[2], ps[3]);
+                    const double2 lo = reinterpret_cast<const double2*>(ps)[0], hi = reinterpret_cast<const double2*>(ps)[1];
+                    reinterpret_cast<double2*>(dst)[0] = lo;
+                    reinterpret_cast<double2*>(dst)[1] = hi;
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -266,14 +296,15 @@ row_sum_small_kernel(const float* __restrict__ covT, int w, int h, int hp, int b
 constexpr int kColChunk = 16;     // y steps per chunk
 constexpr int kColStages = 6;     // stages of operand rows (ring between the loaders and the chains)
 constexpr int kColRing = 4;       // chunks of box sums between the chains and the helpers
-constexpr int kColThreads = 96 + 768, kColHelpers = kColThreads - 96;
+constexpr int kColThreads = 96 + 768, kColHelpers = kColThreads - 96;   // threads that take part in the named barriers
+constexpr int kColBlock = 1024;   // chains = warps 0, 4, 8 (one scheduler to themselves), helpers = the warps of the other three schedulers
 struct ColSmem {
     double st[kColStages][2][3][kColChunk][32];   // [stage][entering / leaving][channel][row][column]
     float t[kColRing][3][kColChunk][32];
 };
 enum { kBarColStFull = 1, kBarColTFull = 1 + kColStages, kBarColTEmpty = 1 + kColStages + kColRing };
 
-__global__ void __launch_bounds__(kColThreads)
+__global__ void __launch_bounds__(kColBlock)
 col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block, float* __restrict__ eig, long long eig_pitch,
                 long long eig_batch_stride, const uint8_t* __restrict__ mask, long long mask_pitch, long long mask_batch_stride,
                 unsigned* __restrict__ max_out)
@@ -287,9 +318,11 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
     const double* __restrict__ R = rows + (long long)blockIdx.z * 3 * plane + x0;
     const int nck = (h + kColChunk - 1) / kColChunk;
 
-    if (wrp < 3) {
-        // ---- chain warps ----
-        const double* __restrict__ Rx = R + wrp * plane + lane;
+    if ((wrp & 3) == 0) {
+        // ---- chain warps: 0, 4, 8 (all on the first warp scheduler, which no helper shares); the rest of that scheduler idles
+        if (wrp > 8) return;
+        const int ch = wrp >> 2;
+        const double* __restrict__ Rx = R + ch * plane + lane;
         double s = 0.0;
         for (int i0 = 0; i0 < block - 1; i0 += 16) {
             double v[16];
@@ -302,9 +335,9 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
         for (int k = 0; k < nck; ++k) {
             bar_sync(kBarColStFull + k % kColStages, kColThreads);                        // operand rows of chunk k staged
             if (k >= kColRing) bar_sync(kBarColTEmpty + k % kColRing, kColThreads);       // chunk k - kColRing turned into eigenvalues
-            const double* __restrict__ pe = &sm.st[k % kColStages][0][wrp][0][lane];
-            const double* __restrict__ pl = &sm.st[k % kColStages][1][wrp][0][lane];
-            float* __restrict__ pt = &sm.t[k % kColRing][wrp][0][lane];
+            const double* __restrict__ pe = &sm.st[k % kColStages][0][ch][0][lane];
+            const double* __restrict__ pl = &sm.st[k % kColStages][1][ch][0][lane];
+            float* __restrict__ pt = &sm.t[k % kColRing][ch][0][lane];
             double ve[kColChunk], vl[kColChunk];   // operands into registers first (see row_scan_kernel)
 #pragma unroll
             for (int j = 0; j < kColChunk; ++j) { ve[j] = pe[j * 32]; vl[j] = pl[j * 32]; }
@@ -320,7 +353,7 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
         return;
     }
     // ---- helper warps: every thread owns 4 fixed 16-byte pieces of each stage and up to 2 pixels of each chunk ----
-    const int ht = tid - 96;
+    const int ht = (wrp - 1 - (wrp >> 2)) * 32 + lane;
     float* __restrict__ E = eig + (long long)blockIdx.z * eig_batch_stride;
     const uint8_t* __restrict__ M = mask ? mask + (long long)blockIdx.z * mask_batch_stride : nullptr;
     constexpr int NRG = kColHelpers / 96;               // row groups: 16 pieces x 6 planes per row
@@ -560,8 +593,8 @@ klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long 
     if (block == 3 || block == 5)
         row_sum_small_kernel<<<dim3((h + 31) / 32, (w + 7) / 8, 3 * batch), dim3(32, 8), 0, stream>>>(covT, w, h, hp, block, rows, wd);
     else
-        row_scan_kernel<<<dim3((h + 31) / 32, 3, batch), kRowThreads, sizeof(RowSmem), stream>>>(covT, w, h, hp, block, rows, wd);
-    col_scan_kernel<<<dim3((w + 31) / 32, 1, batch), kColThreads, sizeof(ColSmem), stream>>>(rows, w, h, wd, block, eig, eig_pitch, eig_batch_stride,
+        row_scan_kernel<<<dim3((h + 31) / 32, 3, batch), kRowBlock, sizeof(RowSmem), stream>>>(covT, w, h, hp, block, rows, wd);
+    col_scan_kernel<<<dim3((w + 31) / 32, 1, batch), kColBlock, sizeof(ColSmem), stream>>>(rows, w, h, wd, block, eig, eig_pitch, eig_batch_stride,
                                                                                          mask, mask_pitch, mask_batch_stride, max_out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
@@ -600,3 +633,12 @@ klt_status corner_sort_launch(const unsigned long long* keys, long long keys_bat
 }
 
 }  // namespace klt
+
+// profiling aid, not part of the ABI of include/klt_b200.h: switch the chain-warp timeline on / read it back
+extern "C" int klt_debug_corner_timeline(int enable, long long* out, int n_words)
+{
+    cudaError_t e = cudaMemcpyToSymbol(klt::g_timeline_on, &enable, sizeof(int));
+    if (e == cudaSuccess && out && n_words > 0)
+        e = cudaMemcpyFromSymbol(out, klt::g_timeline, sizeof(long long) * (size_t)(n_words < 1024 ? n_words : 1024));
+    return (int)e;
+}
