@@ -103,32 +103,34 @@ __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // profiling aid (KLT_CORNER_TIMELINE=1, scripts/corner_timeline.py): clock64 stamps of the chain warp of block (0,0,0)
-__device__ long long g_timeline[4 * 256];
+__device__ long long g_timeline[4 * 256 + 6 * 256];   // chain warp: 4 stamps per chunk; helper warp 0: 6 per chunk from word 1024
 __device__ int g_timeline_on;
 
 // ---- row_scan_kernel ------------------------------------------------------------------------------------------
 // The running sum along x is a serial chain of one DADD per pixel and row, and with so little parallelism (H rows x 3
 // channels) the launch time IS the time of one chain.  So the block is specialised: warp 0 ("chain", lane = row) does
-// nothing but  d = smem, s += d, smem = s;  sixteen helper warps keep everything else off that warp: they stage the two
-// operand columns of each step (entering and leaving the box; each column of the transposed product image is one
-// 128-byte run over the block's 32 rows) with cp.async kRowStages chunks ahead, form d = (double)new - (double)old
-// exactly as OpenCV does, and write the finished sums row-major in 256-byte runs.  The two sides are coupled only by
-// named-barrier signals over rings of kRowRing chunks (d full / s full / s empty), so the chain warp never waits for a
-// block-wide barrier.
-constexpr int kRowChunk = 64;     // x steps per chunk (multiple of 32)
-constexpr int kRowStages = 4;     // cp.async chunks in flight per helper thread
+// nothing but  d = smem, s += d, smem = s;  the helper warps keep everything else off that warp: lane = row for them as
+// well, so a column of the transposed product image is one coalesced 128-byte load; they fetch the entering and the
+// leaving column of each step a chunk ahead (registers), form d = (double)new - (double)old exactly as OpenCV does, and
+// write the finished sums row-major in 256-byte runs.  The two sides are coupled only by named-barrier signals over
+// rings of kRowRing chunks (d full / s full / s empty), and the chain warp has a warp scheduler to itself (warps are
+// dealt to the four schedulers round-robin; the other warps whose index is a multiple of 4 idle).
+// Shared-memory traffic is the budget that matters (chain-warp timeline, scripts/corner_timeline.py): per 64-step chunk
+// the d and s rings cost 4 x 128 wavefronts, the same order as the 512 cycles of the DADD chain; an earlier version
+// that also staged the operands through shared memory (cp.async) and wrote d with a 4-way bank conflict needed ~1150
+// wavefronts and ran at 22 cycles per step.  Rings are lane-major with a row stride of 65 doubles: conflict-free for
+// "32 rows, one column" and for "one row, 32 columns".
+constexpr int kRowChunk = 64;     // x steps per chunk
 constexpr int kRowRing = 4;       // chunks of d / s between the chain warp and the helpers
-constexpr int kRowLag = 2;        // helpers write out chunk c - kRowLag while the chain works on chunk c (<= kRowRing)
-constexpr int kRowHelpers = 512;  // helper threads: the per-chunk latency of a helper is what bounds the chain, so many warps with little work each
+constexpr int kRowLag = 2;        // helpers write out chunk c - kRowLag while the chain works on chunk c (< kRowRing)
+constexpr int kRowHelperWarps = 23;
+constexpr int kRowHelpers = 32 * kRowHelperWarps;
 constexpr int kRowThreads = 32 + kRowHelpers;            // threads that take part in the named barriers
-constexpr int kRowBlock = 32 * (1 + kRowHelpers / 32 + (kRowHelpers / 32 + 2) / 3);   // + idle warps, see below
+constexpr int kRowBlock = 32 * (1 + kRowHelperWarps + (kRowHelperWarps + 2) / 3);   // + idle warps
+constexpr int kRowCPW = (kRowChunk + kRowHelperWarps - 1) / kRowHelperWarps;        // columns per helper warp and chunk
 struct RowSmem {
-    float lead[kRowStages][kRowChunk][32];
-    float trail[kRowStages][kRowChunk][32];
-    // lane-major with a row stride of kRowChunk + 2 doubles (16-byte aligned, an odd number of 16-byte units): the chain
-    // warp moves two steps per 128-bit shared-memory access, conflict-free
-    double d[kRowRing][32][kRowChunk + 2];
-    double s[kRowRing][32][kRowChunk + 2];
+    double d[kRowRing][32][kRowChunk + 1];
+    double s[kRowRing][32][kRowChunk + 1];
 };
 enum { kBarRowDFull = 1, kBarRowSFull = 1 + kRowRing, kBarRowSEmpty = 1 + 2 * kRowRing };
 
@@ -140,18 +142,17 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int y0 = blockIdx.x * 32, c = blockIdx.y;
     const int an = block / 2;
-    const float* __restrict__ S0 = covT + ((long long)blockIdx.z * 3 + c) * w * hp + y0;   // column x: 32 floats at S0 + x * hp
-    double* __restrict__ D = rows + (((long long)blockIdx.z * 3 + c) * h + y0) * wd;        // row r at D + r * wd
+    const float* __restrict__ S = covT + ((long long)blockIdx.z * 3 + c) * w * hp + y0 + lane;   // column x, this lane's row: S[x * hp]
+    double* __restrict__ D = rows + (((long long)blockIdx.z * 3 + c) * h + y0) * wd;              // row r at D + r * wd
     const int nrows = min(32, h - y0);
     const int nck = (w + kRowChunk - 1) / kRowChunk;
     // output o = 0 is the sum of the first `block` padded columns; output o >= 1 adds column o-1+block and drops o-1
 
-    if (tid < 32) {
+    if (wrp == 0) {
         // ---- chain warp ----
-        const float* __restrict__ S = S0 + lane;
         double s = 0.0;
         for (int i0 = 0; i0 < block; i0 += 16) {
             float v[16];
@@ -170,107 +171,107 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             if (tl) g_timeline[4 * k + 1] = clock64();
             if (k >= kRowRing) bar_sync(kBarRowSEmpty + slot, kRowThreads);   // chunk k - kRowRing has been written out
             if (tl) g_timeline[4 * k + 2] = clock64();
-            // 16 steps at a time, the next 16 operands already requested (two register buffers).  Measured (timeline of
-            // scripts/corner_timeline.py): ~22 cycles per step although a dependent DADD takes 8 -- ptxas interleaves the
-            // loads and stores with the chain and gives a load the registers a store has just read, and the in-order issue
-            // of the DADDs waits for that store; fences (one-warp named barriers) around the chain made it worse.
-            const double2* __restrict__ pd = reinterpret_cast<const double2*>(&sm.d[slot][lane][0]);
-            double2* __restrict__ ps = reinterpret_cast<double2*>(&sm.s[slot][lane][0]);
-            double2 buf[2][8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) buf[0][j] = pd[j];
-            if (k == 0) buf[0][0].x = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
+            const double* __restrict__ pd = &sm.d[slot][lane][0];
+            double* __restrict__ ps = &sm.s[slot][lane][0];
 #pragma unroll
             for (int q = 0; q < kRowChunk / 16; ++q) {
-                if (q + 1 < kRowChunk / 16) {
+                double v[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) buf[(q + 1) & 1][j] = pd[8 * (q + 1) + j];
-                }
+                for (int j = 0; j < 16; ++j) v[j] = pd[16 * q + j];
+                if (k == 0 && q == 0) v[0] = 0.0;   // output 0 is the initial sum itself (s + 0.0 == s: s is never -0)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s = __dadd_rn(s, buf[q & 1][j].x); buf[q & 1][j].x = s;
-                    s = __dadd_rn(s, buf[q & 1][j].y); buf[q & 1][j].y = s;
-                }
+                for (int j = 0; j < 16; ++j) { s = __dadd_rn(s, v[j]); v[j] = s; }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ps[8 * q + j] = buf[q & 1][j];
+                for (int j = 0; j < 16; ++j) ps[16 * q + j] = v[j];
             }
             bar_arrive(kBarRowSFull + slot, kRowThreads);
             if (tl) g_timeline[4 * k + 3] = clock64();
         }
         return;
     }
-    // The chain warp gets a warp scheduler to itself: warps are dealt to the four schedulers round-robin, so every
-    // other warp whose index is a multiple of 4 is left idle (timeline: the chain no longer waits for its operands, 250-650
-    // cycles per chunk before).
-    const int wrp = tid >> 5;
-    if ((wrp & 3) == 0) return;
-    // ---- helper warps: thread = 16-byte pieces (4 rows) of kRowChunk / 32 staged columns ----
-    const int ht = (wrp - 1 - (wrp >> 2)) * 32 + lane;
-    if (ht >= kRowHelpers) return;
-    const int pj0 = ht >> 3, part = (ht & 7) * 4;   // first column within the chunk, first of 4 rows
-    constexpr int PJ = kRowHelpers / 8;             // columns staged per pass over the helper threads
-    constexpr int NP = kRowChunk / PJ;
-    static_assert(kRowChunk % PJ == 0 && kRowHelpers % 256 == 0, "helper thread mapping");
-    auto issue = [&](int k) {
-        if (k < nck) {
+    if ((wrp & 3) == 0) return;                       // leave the chain's scheduler alone
+    const int hw = wrp - 1 - (wrp >> 2);              // helper warp index
+    if (hw >= kRowHelperWarps) return;
+    // ---- helper warps: lane = row; helper warp hw owns columns hw, hw + kRowHelperWarps, ... of every chunk ----
+    float leadA[kRowCPW], trailA[kRowCPW], leadB[kRowCPW], trailB[kRowCPW];   // two chunks of operands in flight
+    auto fetch = [&](int k, float (&lead)[kRowCPW], float (&trail)[kRowCPW]) {   // operands of outputs k * kRowChunk + j
+        const int t0 = k * kRowChunk + hw - 1 - an;            // leaving column of this warp's first step (unreflected)
+        if (t0 >= 0 && k * kRowChunk + hw >= 1 && t0 + block + kRowHelperWarps * (kRowCPW - 1) < w) {
+            // interior chunk (all but the first and the last one or two): plain strides, no reflection
+            const float* __restrict__ p = S + (long long)t0 * hp;
+            const long long lead_off = (long long)block * hp, step = (long long)kRowHelperWarps * hp;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int pj = pj0 + PJ * i;
-                const int o = min(max(k * kRowChunk + pj, 1), w - 1 > 1 ? w - 1 : 1);
-                cp_async16(&sm.lead[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1 + block, an, w) * hp + part);
-                cp_async16(&sm.trail[k % kRowStages][pj][part], S0 + (long long)src_col(o - 1, an, w) * hp + part);
+            for (int i = 0; i < kRowCPW; ++i) {
+                trail[i] = p[i * step];
+                lead[i] = p[i * step + lead_off];
             }
+            return;
         }
-        cp_async_commit();
-    };
-    auto convert = [&](int k) {   // the pieces this thread staged itself: no cross-thread dependency
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int pj = pj0 + PJ * i;
-            const float4 a = *reinterpret_cast<const float4*>(&sm.lead[k % kRowStages][pj][part]);
-            const float4 b = *reinterpret_cast<const float4*>(&sm.trail[k % kRowStages][pj][part]);
-            double (*dst)[kRowChunk + 2] = sm.d[k % kRowRing];
-            dst[part + 0][pj] = __dsub_rn((double)a.x, (double)b.x);
-            dst[part + 1][pj] = __dsub_rn((double)a.y, (double)b.y);
-            dst[part + 2][pj] = __dsub_rn((double)a.z, (double)b.z);
-            dst[part + 3][pj] = __dsub_rn((double)a.w, (double)b.w);
+        for (int i = 0; i < kRowCPW; ++i) {
+            const int j = hw + kRowHelperWarps * i;
+            const int o = min(max(k * kRowChunk + j, 1), w - 1 > 1 ? w - 1 : 1);
+            lead[i] = S[(long long)src_col(o - 1 + block, an, w) * hp];
+            trail[i] = S[(long long)src_col(o - 1, an, w) * hp];
         }
     };
-    auto flush = [&](int k) {     // outputs of chunk k: row r = ht / 8, columns (ht % 8) * 4 .. + 3 of every 32-column group
-        const int r = (ht >> 3) & 31;
+    auto convert = [&](int k, const float (&lead)[kRowCPW], const float (&trail)[kRowCPW]) {
+        double* __restrict__ dst = &sm.d[k % kRowRing][lane][0];
+#pragma unroll
+        for (int i = 0; i < kRowCPW; ++i) {
+            const int j = hw + kRowHelperWarps * i;
+            if (j < kRowChunk) dst[j] = __dsub_rn((double)lead[i], (double)trail[i]);
+        }
+    };
+    // the (row, 32-column half) pairs this warp writes out are the same for every chunk: offsets computed once
+    constexpr int NT = 32 * (kRowChunk / 32), NR = (NT + kRowHelperWarps - 1) / kRowHelperWarps;
+    int f_soff[NR], f_c0[NR];
+    long long f_goff[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const int t = hw + kRowHelperWarps * i;
+        const int r = min(t, NT - 1) / (kRowChunk / 32), c0 = 32 * (min(t, NT - 1) % (kRowChunk / 32)) + lane;
+        f_soff[i] = r * (kRowChunk + 1) + c0;
+        f_c0[i] = (t < NT && r < nrows) ? c0 : kRowChunk;      // kRowChunk = never below n: nothing to write
+        f_goff[i] = (long long)r * wd + c0;
+    }
+    auto flush = [&](int k, long long* tl) {     // outputs of chunk k, lane = column: 256-byte runs
         const int xbase = k * kRowChunk, n = min(kRowChunk, w - xbase);
         bar_sync(kBarRowSFull + k % kRowRing, kRowThreads);
-        if (r < nrows) {
+        if (tl) tl[3] = clock64();
+        // all loads first, then all stores: a load into the register a store has just read waits for that store
+        const double* __restrict__ sp = &sm.s[k % kRowRing][0][0];
+        double* __restrict__ gp = D + xbase;
+        double v[NR];
 #pragma unroll
-            for (int i = 0; i < kRowChunk / (kRowHelpers / 8); ++i) {
-                const int c0 = (ht & 7) * 4 + 32 * (ht >> 8) + (kRowHelpers / 8) * i;
-                const double* __restrict__ ps = &sm.s[k % kRowRing][r][c0];
-                double* __restrict__ dst = D + (long long)r * wd + xbase + c0;
-                if (c0 + 3 < n) {
-                    const double2 lo = reinterpret_cast<const double2*>(ps)[0], hi = reinterpret_cast<const double2*>(ps)[1];
-                    reinterpret_cast<double2*>(dst)[0] = lo;
-                    reinterpret_cast<double2*>(dst)[1] = hi;
-                } else {
+        for (int i = 0; i < NR; ++i) v[i] = sp[f_soff[i]];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (c0 + q < n) dst[q] = ps[q];
-                }
-            }
-        }
+        for (int i = 0; i < NR; ++i)
+            if (f_c0[i] < n) gp[f_goff[i]] = v[i];
+        if (tl) tl[4] = clock64();
         if (k + kRowRing < nck) bar_arrive(kBarRowSEmpty + k % kRowRing, kRowThreads);   // the slot may be rewritten
     };
     static_assert(kRowLag + 1 <= kRowRing, "d[slot] is rewritten only after the chain finished the chunk that was in it");
-#pragma unroll
-    for (int k = 0; k < kRowStages; ++k) issue(k);
-    for (int k = 0; k < nck; ++k) {
-        // feed the chain first: d[k % ring] is free because this thread has already seen "s full" of chunk k - 1 - lag
-        cp_async_wait<kRowStages - 1>();     // chunk k has landed (this thread's pieces)
-        convert(k);
+    fetch(0, leadA, trailA);
+    fetch(1, leadB, trailB);
+    const bool htl = g_timeline_on && hw == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    auto step = [&](int k, float (&lead)[kRowCPW], float (&trail)[kRowCPW]) {
+        // feed the chain first: d[k % ring] is free because this warp has already seen "s full" of chunk k - 1 - lag
+        long long* tl = (htl && k < 256) ? g_timeline + 1024 + 6 * k : nullptr;
+        if (tl) tl[0] = clock64();
+        convert(k, lead, trail);
+        if (tl) tl[1] = clock64();
         bar_arrive(kBarRowDFull + k % kRowRing, kRowThreads);
-        issue(k + kRowStages);               // into the staging slot just consumed
-        if (k >= kRowLag) flush(k - kRowLag);
+        if (k + 2 < nck) fetch(k + 2, lead, trail);   // two chunks ahead: the load latency hides behind a whole iteration
+        if (tl) tl[2] = clock64();
+        if (k >= kRowLag) flush(k - kRowLag, tl);
+        if (tl) tl[5] = clock64();
+    };
+    for (int k = 0; k < nck; k += 2) {
+        step(k, leadA, trailA);
+        if (k + 1 < nck) step(k + 1, leadB, trailB);
     }
-    for (int k = max(nck - kRowLag, 0); k < nck; ++k) flush(k);
+    for (int k = max(nck - kRowLag, 0); k < nck; ++k) flush(k, nullptr);
 }
 
 // OpenCV's RowSum forms fresh left-to-right sums for kernel sizes 3 and 5: no chain, one thread per output.
@@ -639,6 +640,6 @@ extern "C" int klt_debug_corner_timeline(int enable, long long* out, int n_words
 {
     cudaError_t e = cudaMemcpyToSymbol(klt::g_timeline_on, &enable, sizeof(int));
     if (e == cudaSuccess && out && n_words > 0)
-        e = cudaMemcpyFromSymbol(out, klt::g_timeline, sizeof(long long) * (size_t)(n_words < 1024 ? n_words : 1024));
+        e = cudaMemcpyFromSymbol(out, klt::g_timeline, sizeof(long long) * (size_t)(n_words < 2560 ? n_words : 2560));
     return (int)e;
 }
