@@ -8,7 +8,8 @@ L = _lib.load()
 L.klt_debug_corner_timeline.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
 a = S.frame_pair(376, 1241, seed=3)[0]
 for _ in range(3): K.cornerMinEigenVal(a, 31)
-assert L.klt_debug_corner_timeline(1, None, 0) == 0
+mode = 2 if 'col' in sys.argv else 1   # 1 = row_scan_kernel, 2 = col_scan_kernel
+assert L.klt_debug_corner_timeline(mode, None, 0) == 0
 K.cornerMinEigenVal(a, 31)
 buf = np.zeros(2560, np.int64)
 assert L.klt_debug_corner_timeline(0, buf.ctypes.data, 2560) == 0

@@ -162,7 +162,7 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
             for (int i = 0; i < 16; ++i)
                 if (i0 + i < block) s = __dadd_rn(s, (double)v[i]);
         }
-        const bool tl_on = g_timeline_on && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        const bool tl_on = g_timeline_on == 1 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
         for (int k = 0; k < nck; ++k) {
             const int slot = k % kRowRing;
             const bool tl = tl_on && k < 256;
@@ -254,7 +254,7 @@ row_scan_kernel(const float* __restrict__ covT, int w, int h, int hp, int block,
     static_assert(kRowLag + 1 <= kRowRing, "d[slot] is rewritten only after the chain finished the chunk that was in it");
     fetch(0, leadA, trailA);
     fetch(1, leadB, trailB);
-    const bool htl = g_timeline_on && hw == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const bool htl = g_timeline_on == 1 && hw == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     auto step = [&](int k, float (&lead)[kRowCPW], float (&trail)[kRowCPW]) {
         // feed the chain first: d[k % ring] is free because this warp has already seen "s full" of chunk k - 1 - lag
         long long* tl = (htl && k < 256) ? g_timeline + 1024 + 6 * k : nullptr;
@@ -333,23 +333,35 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
             for (int i = 0; i < 16; ++i)
                 if (i0 + i < block - 1) s = __dadd_rn(s, v[i]);
         }
+        const bool tl_on = g_timeline_on == 2 && wrp == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.z == 0;
         for (int k = 0; k < nck; ++k) {
+            const bool tl = tl_on && k < 256;
+            if (tl) g_timeline[4 * k] = clock64();
             bar_sync(kBarColStFull + k % kColStages, kColThreads);                        // operand rows of chunk k staged
+            if (tl) g_timeline[4 * k + 1] = clock64();
             if (k >= kColRing) bar_sync(kBarColTEmpty + k % kColRing, kColThreads);       // chunk k - kColRing turned into eigenvalues
+            if (tl) g_timeline[4 * k + 2] = clock64();
             const double* __restrict__ pe = &sm.st[k % kColStages][0][ch][0][lane];
             const double* __restrict__ pl = &sm.st[k % kColStages][1][ch][0][lane];
             float* __restrict__ pt = &sm.t[k % kColRing][ch][0][lane];
-            double ve[kColChunk], vl[kColChunk];   // operands into registers first (see row_scan_kernel)
+            // 8 steps at a time: the block has 1024 threads, i.e. 64 registers per thread -- with all 32 operands of a chunk
+            // "in registers first" ptxas had to reload just in time and every step paid a shared-memory latency (timeline: 52
+            // cycles per step for two dependent DADDs)
 #pragma unroll
-            for (int j = 0; j < kColChunk; ++j) { ve[j] = pe[j * 32]; vl[j] = pl[j * 32]; }
+            for (int g = 0; g < kColChunk / 8; ++g) {
+                double ve[8], vl[8];
 #pragma unroll
-            for (int j = 0; j < kColChunk; ++j) {
-                ve[j] = __dadd_rn(s, ve[j]);
-                s = __dsub_rn(ve[j], vl[j]);
+                for (int j = 0; j < 8; ++j) { ve[j] = pe[(8 * g + j) * 32]; vl[j] = pl[(8 * g + j) * 32]; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    ve[j] = __dadd_rn(s, ve[j]);
+                    s = __dsub_rn(ve[j], vl[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pt[(8 * g + j) * 32] = __double2float_rn(ve[j]);
             }
-#pragma unroll
-            for (int j = 0; j < kColChunk; ++j) pt[j * 32] = __double2float_rn(ve[j]);
             bar_arrive(kBarColTFull + k % kColRing, kColThreads);   // also: this chain is done with the stage
+            if (tl) g_timeline[4 * k + 3] = clock64();
         }
         return;
     }
@@ -405,14 +417,21 @@ col_scan_kernel(const double* __restrict__ rows, int w, int h, int wd, int block
 #pragma unroll
     for (int k = 0; k < kColStages - 2; ++k) issue(k);
     unsigned mc0 = 1u, mc1 = 1u;
+    const bool htl = g_timeline_on == 2 && ht == 0 && blockIdx.x == 0 && blockIdx.z == 0;
     for (int k = 0; k < nck; ++k) {
         // feed the chains first, then finish chunk k - 2 (two chunks of slack before they could starve)
+        long long* tl = (htl && k < 256) ? g_timeline + 1024 + 6 * k : nullptr;
+        if (tl) tl[0] = clock64();
         cp_async_wait<kColStages - 3>();       // chunk k has landed (this thread's pieces)
+        if (tl) tl[1] = clock64();
         bar_arrive(kBarColStFull + k % kColStages, kColThreads);
         unsigned mn0, mn1;
         load_mask(k - 1, mn0, mn1);            // consumed one iteration later: the load latency hides behind the waits
+        if (tl) tl[2] = clock64();
         if (k >= 2) finish(k - 2, mc0, mc1);   // implies: the chains are done with the stage of chunk k - 2 ...
+        if (tl) tl[3] = clock64();
         issue(k + kColStages - 2);             // ... which is the stage this refills
+        if (tl) { tl[4] = clock64(); tl[5] = tl[4]; }
         mc0 = mn0; mc1 = mn1;
     }
     if (nck >= 2) {
