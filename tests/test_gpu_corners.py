@@ -183,3 +183,32 @@ def test_reference_frame_loop_malaga_shape(klt, cv2):
         assert l1.shape == l2.shape and np.array_equal(l1.view(np.uint32), l2.view(np.uint32)), "landmarks differ at frame %d" % (t + 1)
         assert c1.shape == c2.shape and np.array_equal(c1.view(np.uint32), c2.view(np.uint32)), "candidates differ at frame %d" % (t + 1)
     assert len(got[-1][0]) + len(got[-1][1]) > 2000
+
+
+def test_opt_in_device_selection_kernel_matches_cv2(klt):
+    """KLT_DEVICE_SELECT=1 moves the greedy minimum-distance selection into select_corners_kernel (kept for A/B runs: it
+    loses to the host loop on B200).  Same corners, same order; cases it declines (4K frame: the bitmap
+    does not fit in shared memory, > 8192 candidates, radius > 63) fall through to the host path."""
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, cv2, sys
+sys.path.insert(0, %r)
+import visual_odom_pipeline_b200 as K
+from visual_odom_pipeline_b200 import synth as S
+rng = np.random.default_rng(1)
+for hw in [(376, 1241), (768, 1024), (120, 161), (2160, 3840)]:
+    img = S.frame_pair(hw[0], hw[1], seed=5)[0]
+    mask = np.full(img.shape, 255, np.uint8)
+    for _ in range(40):
+        cv2.circle(mask, (int(rng.integers(0, hw[1])), int(rng.integers(0, hw[0]))), 10, 0, -1)
+    for (mc, ql, md, m, bs) in [(1000, 0.03, 10, mask, 31), (0, 0.01, 3.5, None, 7), (300, 0.02, 25.5, mask, 31), (0, 0.05, 1.0, None, 3), (50, 0.01, 80, None, 31)]:
+        if hw[0] > 2000 and bs != 31:
+            continue
+        c = K.goodFeaturesToTrack(img, mc, ql, md, mask=m, blockSize=bs)
+        k = cv2.goodFeaturesToTrack(img, mc, ql, md, mask=m, blockSize=bs)
+        assert (c is None and k is None) or (c.shape == k.shape and np.array_equal(c, k)), (hw, mc, ql, md, bs)
+print("device selection ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KLT_DEVICE_SELECT="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "device selection ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

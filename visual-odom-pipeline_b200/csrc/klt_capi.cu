@@ -714,7 +714,7 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
     const size_t direct_cap = std::min<size_t>(n_px, 1u << 16);
     const size_t off_img = 0, off_mask = off_img + img_bytes, off_eig = off_mask + mask_bytes, off_ws = off_eig + eig_bytes;
     const size_t off_cnt = off_ws + ws_bytes, off_keys = off_cnt + 256 + 8192 * 4;   // max, count, ranks (zeroed per call)
-    klt_status s = ensure_device_ws(ctx, off_keys + (n_px + direct_cap + 1) * 8);
+    klt_status s = ensure_device_ws(ctx, off_keys + (n_px + 8192 + 1 + direct_cap + 1) * 8);   // keys | sorted | results (opt-in path)
     if (s != KLT_OK) return s;
     s = ensure_host_ws(ctx, 8 + direct_cap * 8);
     if (s != KLT_OK) return s;
@@ -746,6 +746,35 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
     if (s != KLT_OK) return s;
     if (trace) cudaStreamSynchronize(st);
     const auto t2 = now();
+    // Opt-in (KLT_DEVICE_SELECT=1): greedy minimum-distance selection on the device as well (select_corners_kernel).
+    // Measured on B200 it LOSES to the host: one block resolves ~128 candidates per window with barriers, ballots and
+    // shared-memory latencies in every window (~170 us per KITTI frame against ~75 us for the sequential host loop), so
+    // the default keeps the selection on the host and the kernel stays for A/B runs.
+    static const bool device_select = getenv("KLT_DEVICE_SELECT") != nullptr;
+    if (device_select && min_distance >= 1) {
+        constexpr size_t kSortedCap = 8192;
+        unsigned long long* dk = reinterpret_cast<unsigned long long*>(d + off_keys);
+        unsigned long long* d_sorted = dk + n_px;                        // header + kSortedCap keys
+        unsigned long long* d_res = d_sorted + (kSortedCap + 1);         // header + direct_cap corners
+        s = corner_candidates_launch(d_eig, w, 0, w, h, 1, d_mask, mpitch, 0, d_max, quality_level, dk, 0, (int)n_px, d_count, st);
+        if (s != KLT_OK) return s;
+        s = corner_sort_launch(dk, 0, d_count, 1, reinterpret_cast<unsigned*>(d + off_cnt + 256), d_sorted, 0, (int)kSortedCap, st);
+        if (s != KLT_OK) return s;
+        s = corner_select_launch(d_sorted, 0, w, h, 1, min_distance, max_corners, d_res, 0, (int)direct_cap, st);
+        if (s != KLT_OK) return s;
+        KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, d_res, 8 + direct_cap * 8, cudaMemcpyDeviceToHost, st));
+        KLT_CUDA(cudaStreamSynchronize(st));
+        const uint64_t hdr = *reinterpret_cast<const uint64_t*>(ctx->h_ws);
+        if (hdr >> 63) {
+            const int nc = (int)(hdr & 0xffffffffu);
+            const int ncopy = nc < capacity ? nc : capacity;
+            if ((size_t)ncopy > direct_cap) return KLT_ERR_INTERNAL;
+            std::memcpy(corners, ctx->h_ws + 8, (size_t)ncopy * 8);
+            *n_out = nc;
+            return KLT_OK;
+        }
+        KLT_CUDA(cudaMemsetAsync(d_max + 1, 0, 4 + 248 + 8192 * 4, st));   // declined: count and ranks again for the default path
+    }
     // candidates -> device list (one slot per pixel: cannot overflow) -> sorted on the device -> written, with their
     // count, straight into the context's page-locked staging buffer (mapped into the device address space): no copy op
     unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(d + off_keys);
@@ -774,7 +803,7 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
     const auto t3 = now();
     s = select_corners(h_keys, (int64_t)count, sorted, w, h, max_corners, min_distance, corners, capacity, n_out);
     if (trace)
-        std::fprintf(stderr, "[klt trace] gftt: h2d done +%.1f us, eigenvalue kernels +%.1f us, candidates + count sync +%.1f us (%u candidates), host sort + selection %.1f us\n",
+        std::fprintf(stderr, "[klt trace] gftt: h2d done +%.1f us, eigenvalue kernels +%.1f us, candidates + sort + sync +%.1f us (%u candidates), host sort + selection %.1f us\n",
                      us(t0, t1), us(t1, t2), us(t2, t3), count, us(t3, now()));
     return s;
 }

@@ -90,5 +90,11 @@ klt_status corner_candidates_launch(const float* eig, long long eig_pitch, long 
 klt_status corner_sort_launch(const unsigned long long* keys, long long keys_batch_stride, const unsigned* count, int batch,
                               unsigned* rank, unsigned long long* out, long long out_batch_stride, int out_capacity,
                               cudaStream_t stream);
+// greedy minimum-distance selection on the device (one block per image) from the sorted list of corner_sort_launch;
+// out[0] = bit 63 (done here) | corner count, or the candidate count with bit 63 clear (host has to do it), corners as
+// float2 from out[1]
+klt_status corner_select_launch(const unsigned long long* sorted, long long sorted_batch_stride, int w, int h, int batch,
+                                double min_distance, int max_corners, unsigned long long* out, long long out_batch_stride,
+                                int out_capacity, cudaStream_t stream);
 
 }  // namespace klt
