@@ -330,3 +330,24 @@ def test_integer_shift_is_recovered_at_kitti_size(klt):
     d = (q - p).reshape(-1, 2)[ok]
     assert np.abs(d - np.array([dx, dy], np.float32)).max() < 0.05
     assert (er.ravel()[ok] < 1.0).all()
+
+
+def test_opt_in_fused_two_level_pyrdown_is_bit_exact(klt):
+    """KLT_PYR_FUSE=1 builds levels >= 1 two at a time (pyr_down2_kernel; off by default, it measured slower)."""
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, cv2, sys
+sys.path.insert(0, %r)
+import visual_odom_pipeline_b200 as K
+from visual_odom_pipeline_b200 import synth as S
+for hw in [(376, 1241), (480, 640), (135, 241), (97, 203), (2160, 3840)]:
+    img = S.texture(hw[0], hw[1], seed=hw[1]).astype(np.uint8)
+    top, levels = K.buildOpticalFlowPyramid(img, (5, 5), 6)
+    ref = img
+    for l in range(1, top + 1):
+        ref = cv2.pyrDown(ref)
+        assert np.array_equal(levels[l], ref), (hw, l)
+print("fused pyramid ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, KLT_PYR_FUSE="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fused pyramid ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

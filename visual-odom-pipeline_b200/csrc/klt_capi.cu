@@ -257,6 +257,16 @@ klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layou
         const klt_level& b = layout->level[l + 1];
         if (b.w != (a.w + 1) / 2 || b.h != (a.h + 1) / 2) return KLT_ERR_INVALID_ARG;
         const uint8_t* src = ((l == 0) ? d_img : d_pyr + a.offset) + (int64_t)first_item * a.batch_stride;
+        if (l >= 1 && l + 2 <= layout->top) {
+            // levels >= 1 are small: two of them per launch (level 0 -> 1 stays with the HBM-bound streaming kernel)
+            const klt_level& c = layout->level[l + 2];
+            if (c.w != (b.w + 1) / 2 || c.h != (b.h + 1) / 2) return KLT_ERR_INVALID_ARG;
+            s = pyr_down2_launch(src, a.w, a.h, a.pitch, a.batch_stride, d_pyr + b.offset + (int64_t)first_item * b.batch_stride, b.pitch,
+                                 b.batch_stride, d_pyr + c.offset + (int64_t)first_item * c.batch_stride, c.pitch, c.batch_stride, n_items,
+                                 (cudaStream_t)stream);
+            if (s == KLT_OK) { ++l; continue; }
+            if (s != KLT_ERR_UNSUPPORTED) return s;
+        }
         s = pyr_down_launch(src, a.w, a.h, a.pitch, a.batch_stride, d_pyr + b.offset + (int64_t)first_item * b.batch_stride,
                             b.pitch, b.batch_stride, n_items, ctx->sm_count, (cudaStream_t)stream);
         if (s != KLT_OK) return s;

@@ -44,6 +44,11 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
                            uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
                            cudaStream_t stream);
 
+// Two pyramid levels (l -> l+1 -> l+2) in one launch; KLT_ERR_UNSUPPORTED for shapes it does not take.
+klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0, long long batch0,
+                            uint8_t* mid, long long pitch1, long long batch1, uint8_t* dst, long long pitch2, long long batch2,
+                            int batch, cudaStream_t stream);
+
 // Copies n_img tightly/oddly pitched u8 images (image i at src + i * sbatch, rows spitch apart, any alignment) into
 // 16-byte-aligned pitched storage.  The source buffer must be readable up to 16 bytes past the last pixel.
 klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,

@@ -846,6 +846,100 @@ klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
+// ---- two pyramid levels in one launch (experiment, off by default; see pyr_down2_launch) ----------------------------
+// A block produces a 32 x 8 tile of level l+2 and the 64 x 16 tile of level l+1 below it.  The level l+1 region it needs
+// (67 x 19 with the 5-tap halo) is computed from a 137 x 41 region of level l in shared memory; positions of that region
+// outside the level l+1 image are filled by REFLECT_101 of the level l+1 image itself (a pyrDown of the reflected level l
+// pixels would be a different value).  Integer arithmetic as in pyr_down_kernel: bit-exact with OpenCV.
+namespace {
+constexpr int kP2TX = 32, kP2TY = 8;                 // level l+2 tile
+constexpr int kP2MW = 2 * kP2TX + 3, kP2MH = 2 * kP2TY + 3;   // level l+1 region: 67 x 19
+constexpr int kP2SW = 2 * kP2MW + 3, kP2SH = 2 * kP2MH + 3;   // level l region: 137 x 41
+
+__global__ void __launch_bounds__(256)
+pyr_down2_kernel(const uint8_t* __restrict__ src, int w0, int h0, long long pitch0, long long batch0,
+                 uint8_t* __restrict__ mid, int w1, int h1, long long pitch1, long long batch1,
+                 uint8_t* __restrict__ dst, int w2, int h2, long long pitch2, long long batch2)
+{
+    __shared__ uint8_t sS[kP2SH][kP2SW + 3];
+    __shared__ uint16_t sH[kP2SH][kP2MW + 1];      // horizontal pass of level l -> l+1 (<= 16 * 255)
+    __shared__ uint8_t sM[kP2MH][kP2MW + 1];
+    __shared__ uint16_t sH2[kP2MH][kP2TX];
+    const int tid = threadIdx.x;
+    const int X2 = blockIdx.x * kP2TX, Y2 = blockIdx.y * kP2TY;
+    const int mx0 = 2 * X2 - 2, my0 = 2 * Y2 - 2;    // level l+1 coordinate of sM[0][0]
+    const int sx0 = 2 * mx0 - 2, sy0 = 2 * my0 - 2;  // level l coordinate of sS[0][0]
+    const uint8_t* __restrict__ S = src + (long long)blockIdx.z * batch0;
+    for (int i = tid; i < kP2SH * kP2SW; i += 256) {
+        const int r = i / kP2SW, c = i - r * kP2SW;
+        sS[r][c] = __ldg(S + (long long)reflect101(sy0 + r, h0) * pitch0 + reflect101(sx0 + c, w0));
+    }
+    __syncthreads();
+    for (int i = tid; i < kP2SH * kP2MW; i += 256) {
+        const int r = i / kP2MW, c = i - r * kP2MW;
+        const uint8_t* q = &sS[r][2 * c];
+        sH[r][c] = (uint16_t)(q[0] + q[4] + 4 * (q[1] + q[3]) + 6 * q[2]);
+    }
+    __syncthreads();
+    uint8_t* __restrict__ Mo = mid + (long long)blockIdx.z * batch1;
+    for (int i = tid; i < kP2MH * kP2MW; i += 256) {
+        const int r = i / kP2MW, c = i - r * kP2MW;
+        const int x1 = mx0 + c, y1 = my0 + r;
+        if ((unsigned)x1 < (unsigned)w1 && (unsigned)y1 < (unsigned)h1) {
+            const int v = (sH[2 * r][c] + sH[2 * r + 4][c] + 4 * (sH[2 * r + 1][c] + sH[2 * r + 3][c]) + 6 * sH[2 * r + 2][c] + 128) >> 8;
+            sM[r][c] = (uint8_t)v;
+            if (r >= 2 && r < 2 + 2 * kP2TY && c >= 2 && c < 2 + 2 * kP2TX) Mo[(long long)y1 * pitch1 + x1] = (uint8_t)v;   // the tile this block owns
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < kP2MH * kP2MW; i += 256) {   // outside the level l+1 image: REFLECT_101 of that image
+        const int r = i / kP2MW, c = i - r * kP2MW;
+        const int x1 = mx0 + c, y1 = my0 + r;
+        if (!((unsigned)x1 < (unsigned)w1 && (unsigned)y1 < (unsigned)h1)) {
+            const int xr = reflect101(x1, w1) - mx0, yr = reflect101(y1, h1) - my0;
+            // positions whose mirror image lies outside the region are never read by a valid output of this block
+            sM[r][c] = ((unsigned)xr < (unsigned)kP2MW && (unsigned)yr < (unsigned)kP2MH) ? sM[yr][xr] : (uint8_t)0;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < kP2MH * kP2TX; i += 256) {
+        const int r = i / kP2TX, c = i - r * kP2TX;
+        const uint8_t* q = &sM[r][2 * c];
+        sH2[r][c] = (uint16_t)(q[0] + q[4] + 4 * (q[1] + q[3]) + 6 * q[2]);
+    }
+    __syncthreads();
+    {
+        const int c = tid & 31, r = tid >> 5;    // 32 x 8 outputs, one per thread
+        const int x2 = X2 + c, y2 = Y2 + r;
+        if (x2 < w2 && y2 < h2) {
+            const int v = (sH2[2 * r][c] + sH2[2 * r + 4][c] + 4 * (sH2[2 * r + 1][c] + sH2[2 * r + 3][c]) + 6 * sH2[2 * r + 2][c] + 128) >> 8;
+            dst[(long long)blockIdx.z * batch2 + (long long)y2 * pitch2 + x2] = (uint8_t)v;
+        }
+    }
+}
+}  // namespace
+
+// levels l -> l+1 -> l+2 in one launch; KLT_ERR_UNSUPPORTED when the shapes do not allow it (caller uses two launches)
+klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0, long long batch0,
+                            uint8_t* mid, long long pitch1, long long batch1, uint8_t* dst, long long pitch2, long long batch2,
+                            int batch, cudaStream_t stream)
+{
+    if (!src || !mid || !dst || w0 <= 0 || h0 <= 0 || batch <= 0) return KLT_ERR_INVALID_ARG;
+    const int w1 = (w0 + 1) / 2, h1 = (h0 + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
+    // the mirror image of an out-of-image level l+1 position must lie inside the block's region: guaranteed when the
+    // level l+1 image is at least 4 wide / high (smaller ones take the single-level kernels)
+    if (w1 < 4 || h1 < 4 || batch > 65535 || (h2 + kP2TY - 1) / kP2TY > 65535) return KLT_ERR_UNSUPPORTED;
+    // Opt-in (KLT_PYR_FUSE=1, A/B runs): measured on B200 this simple tile kernel (byte loads, byte-wide shared memory)
+    // LOSES to two launches of the streaming kernel -- whole pyramid of 310 KITTI frames 187 us against 69 us, a single
+    // pair 20.7 us against 17.1 us -- so the default stays one launch per level.
+    static const char* on = getenv("KLT_PYR_FUSE");
+    if (!(on && on[0] == '1')) return KLT_ERR_UNSUPPORTED;
+    pyr_down2_kernel<<<dim3((w2 + kP2TX - 1) / kP2TX, (h2 + kP2TY - 1) / kP2TY, batch), 256, 0, stream>>>(
+        src, w0, h0, pitch0, batch0, mid, w1, h1, pitch1, batch1, dst, w2, h2, pitch2, batch2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
 klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, long long sbatch,
                            uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
                            cudaStream_t stream)
