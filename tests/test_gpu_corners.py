@@ -212,3 +212,30 @@ print("device selection ok")
     env = dict(os.environ, KLT_DEVICE_SELECT="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "device selection ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_detection_is_deterministic_and_independent_of_candidate_order(klt, cv2):
+    """The candidate list is appended with atomics (arbitrary order); the device sort makes the result a function of the
+    image alone: repeated calls give identical corner lists, and so does a call on a context that ran other work."""
+    img = S.frame_pair(376, 1241, seed=21)[0]
+    mask = discs_mask(cv2, img.shape, 50, 3)
+    ref = cv2.goodFeaturesToTrack(img, 1000, 0.03, 10, mask=mask, blockSize=31)
+    runs = [klt.goodFeaturesToTrack(img, 1000, 0.03, 10, mask=mask, blockSize=31) for _ in range(5)]
+    other = S.frame_pair(480, 640, seed=2)[0]
+    klt.goodFeaturesToTrack(other, 300, 0.01, 5, blockSize=7)          # grows / reuses the context workspace differently
+    runs.append(klt.goodFeaturesToTrack(img, 1000, 0.03, 10, mask=mask, blockSize=31))
+    for r in runs:
+        assert same(r, ref)
+
+
+def test_eigenvalue_map_properties_at_full_size(klt):
+    """Size-independent properties at the stress shape (3840 x 2160): flipping the frame flips the map (the running sums
+    follow the flipped order, so this is a tolerance check, not bit-exact), a constant frame gives an all-zero map, and
+    the map is non-negative up to rounding."""
+    img = S.frame_pair(2160, 3840, seed=4)[0]
+    e = klt.cornerMinEigenVal(img, 31)
+    ef = klt.cornerMinEigenVal(np.ascontiguousarray(img[::-1, ::-1]), 31)[::-1, ::-1]
+    scale = float(e.max())
+    assert scale > 0 and np.abs(e - ef).max() <= 1e-5 * scale          # tolerance: float32 sums in a different order
+    assert e.min() >= -1e-6 * scale
+    assert not klt.cornerMinEigenVal(np.full((2160, 3840), 200, np.uint8), 31).any()
