@@ -529,7 +529,7 @@ candidates_kernel(const float* __restrict__ eig, long long eig_pitch, long long 
 // than kSortMax candidates (plateaus of equal eigenvalues, 4K frames) are passed through unsorted (sorted = 0) and
 // the host sorts them.
 constexpr int kSortMax = 8192;
-constexpr int kRankI = 256, kRankJ = 512;
+constexpr int kRankI = 256, kRankJ = 256;
 
 __global__ void __launch_bounds__(kRankI / 2)
 rank_keys_kernel(const unsigned long long* __restrict__ keys, long long keys_batch_stride, const unsigned* __restrict__ count,
