@@ -4,19 +4,23 @@
 //
 // Arithmetic: oracle/gftt_oracle.c G.1-G.7 (float32 Sobel with OpenCV's AVX2 fused-multiply-add pattern, float32
 // products, DOUBLE running box sums in OpenCV's order, non-fused eigenvalue formula) -- bit-exact with the cv2 wheel.
-// Four kernels per image batch:
+// Kernels per image batch:
 //   cov_kernel        32x32 pixel tiles: u8 tile + halo in shared memory -> Dx, Dy -> (Dx^2, DxDy, Dy^2), written
 //                     TRANSPOSED ([channel][x][y]) so that the row scan reads it coalesced;
-//   row_scan_kernel   one lane per image row (a warp = 32 rows of one channel): the serial double-precision running
-//                     sum along x (the order is part of the result: the sums are not exact); operands staged with
-//                     cp.async several chunks ahead, results transposed through shared memory and written row-major;
-//   col_scan_kernel   one lane per image column, the three channels as three independent chains: running sum along
-//                     y (operand rows staged with cp.async), float32 conversion, eigenvalue, masked maximum (REDUX +
-//                     one atomicMax per warp);
+//   row_scan_kernel   one lane per image row (a block = 32 rows of one channel): the serial double-precision running
+//                     sum along x (the order is part of the result: the sums are not exact) on a "chain" warp that has
+//                     a warp scheduler to itself; helper warps fetch the operands two chunks ahead, form the per-step
+//                     differences and write the sums out; named-barrier signals over rings of chunks;
+//   col_scan_kernel   one lane per image column, three chain warps (one per channel) on one scheduler: running sum along
+//                     y (operand rows staged by helper warps with cp.async), float32 conversion, eigenvalue, masked
+//                     maximum (REDUX + one atomicMax per warp);
 //   candidates_kernel threshold (maxVal * qualityLevel), 3x3 dilation and local-maximum test fused; survivors are
-//                     appended as 64-bit keys (ordered float << 32 | y << 16 | x) with one atomicAdd per 32x32 tile.
-// The sort of the (few thousand) keys and the greedy minimum-distance selection (G.8) are inherently sequential
-// and run on the host (klt_capi.cu), like the tail of cv::cuda::GoodFeaturesToTrackDetector.
+//                     appended as 64-bit keys (ordered float << 32 | y << 16 | x) with one atomicAdd per 32x32 tile;
+//   rank_keys_kernel, scatter_keys_kernel   chip-wide rank sort of the (<= 8192) keys, written with their count into
+//                     page-locked host memory mapped into the device address space.
+// The greedy minimum-distance selection (G.8) is sequential in priority order and runs on the host (klt_capi.cu), like
+// the tail of cv::cuda::GoodFeaturesToTrackDetector; select_corners_kernel is the measured-and-rejected device version
+// (opt-in, KLT_DEVICE_SELECT=1).  DESIGN.md s4 K5 has the measurements behind each of these choices.
 #include "klt_common.cuh"
 
 namespace klt {
