@@ -448,6 +448,15 @@ def main():
             for r_ in range(dreps):
                 K.goodFeaturesToTrack(dimgs[r_ % n_host], mask=dmask, device=local_rank, **det_kw)
             det_ms = 1e3 * (time.perf_counter() - t0) / dreps
+            # the same step with the mask rasterised on the device from the tracked keypoints (opt-in fused call)
+            tracked = K.pinned_empty((n, 2), np.float32)
+            tracked[...] = hp[0][2].reshape(-1, 2)
+            for r_ in range(5):
+                K.detectNewFeatures(dimgs[r_ % n_host], tracked, 10, device=local_rank, **det_kw)
+            t0 = time.perf_counter()
+            for r_ in range(dreps):
+                K.detectNewFeatures(dimgs[r_ % n_host], tracked, 10, device=local_rank, **det_kw)
+            det_pts_ms = 1e3 * (time.perf_counter() - t0) / dreps
             # device-resident, batched eigenvalue maps (the kernels only): 64 frames per launch sequence
             nbd = min(64, 2 * P)
             de = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -461,6 +470,10 @@ def main():
             detection = {"api": "visual_odom_pipeline_b200.goodFeaturesToTrack(numpy pinned image, mask, %s) -> numpy" % det_kw,
                          "e2e_ms_per_frame": det_ms, "frames_per_sec": 1e3 / det_ms, "corners": 0 if got is None else int(len(got)),
                          "h2d_bytes_per_frame": 2 * w * h,
+                         "fused_from_tracked_points": {"api": "visual_odom_pipeline_b200.detectNewFeatures(image, %d tracked keypoints, mask_radius=10)" % n,
+                                                       "e2e_ms_per_frame": det_pts_ms, "h2d_bytes_per_frame": w * h + 8 * n,
+                                                       "note": "mask of extractor.py:102-107 rasterised on the device; the reference additionally spends "
+                                                               "a Python loop over cv2.circle per tracked keypoint building it on the host"},
                          "batched_min_eig": {"frames": nbd, "ms": eig_ms, "us_per_frame": 1e3 * eig_ms / nbd,
                                              "mpixels_per_sec": nbd * w * h / (eig_ms * 1e-3) / 1e6,
                                              "algorithmic_bytes_per_frame": 5 * w * h,

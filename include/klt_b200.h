@@ -183,6 +183,12 @@ klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_p
                         const uint32_t* d_max, double quality_level, uint64_t* d_keys, int64_t keys_batch_stride,
                         int capacity, uint32_t* d_count, void* stream);
 
+/* The detection mask of reference src/extractor/extractor.py:102-107, built on the device: 255 everywhere, then a
+ * filled cv2.circle(mask, np.int32((x, y)), radius, 0, -1) around each of the n points (float32 x, y pairs, device).
+ * Bit-identical to OpenCV's filled circle (midpoint circle), centres outside the image included.  radius <= 127. */
+klt_status klt_corner_mask_from_points(klt_ctx* ctx, const float* d_points, int n, int radius, int w, int h,
+                        uint8_t* d_mask, int64_t mask_pitch, void* stream);
+
 /* The sequential tail of goodFeaturesToTrack on the HOST: sorts the keys of klt_corner_candidates in place (strongest
  * first, equal values: the later pixel in raster order first, like OpenCV) and runs the greedy minimum-distance
  * selection.  corners: capacity x (x, y) floats; *n_out = corners found (<= max_corners if max_corners > 0). */
@@ -198,6 +204,14 @@ klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64
  * 0).  KLT_ERR_INVALID_ARG where cv2 asserts (quality_level <= 0, min_distance < 0, max_corners < 0). */
 klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
                         const uint8_t* mask, int64_t mask_pitch, int max_corners, double quality_level,
+                        double min_distance, int block_size, float* corners, int capacity, int* n_out);
+
+/* Caller-side fusion of the reference's extract() step (src/extractor/extractor.py:102-111): instead of a host mask the
+ * caller passes the keypoints it tracks (HOST float32 x, y pairs) and mask_radius; the mask is rasterised on the device
+ * (klt_corner_mask_from_points), so the call uploads n_points * 8 bytes instead of a w x h mask.  Same result as
+ * building the mask with cv2.circle and calling klt_good_features_to_track_host. */
+klt_status klt_good_features_to_track_points_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                        const float* points, int n_points, int mask_radius, int max_corners, double quality_level,
                         double min_distance, int block_size, float* corners, int capacity, int* n_out);
 
 #ifdef __cplusplus

@@ -248,3 +248,49 @@ int klt_oracle_good_features_to_track(const uint8_t* img, int w, int h, int64_t 
     free(eig);
     return rc;
 }
+
+/* ---- mask of filled circles (reference src/extractor/extractor.py:102-107) --------------------------------------
+ * mask[:] = 255; for every tracked keypoint (x, y) = np.int32(kp.uv): cv2.circle(mask, (x, y), radius, 0, -1).
+ * cv2.circle with thickness -1, LINE_8, shift 0 is OpenCV's midpoint circle (modules/imgproc/src/drawing.cpp, Circle()):
+ * for every step (dx, dy) of the octant walk it fills rows cy -+ dy over [cx - dx, cx + dx] and rows cy -+ dx over
+ * [cx - dy, cx + dy], clipped to the image.  half[d] below is the resulting half-width of row cy +- d. */
+int klt_oracle_circle_half_widths(int radius, int* half /* radius + 1 entries */)
+{
+    if (radius < 0 || !half) return -1;
+    for (int i = 0; i <= radius; ++i) half[i] = -1;
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        if (dx > half[dy]) half[dy] = dx;     /* rows cy -+ dy: [cx - dx, cx + dx] */
+        if (dy > half[dx]) half[dx] = dy;     /* rows cy -+ dx: [cx - dy, cx + dy] */
+        dy++;
+        err += plus;
+        plus += 2;
+        const int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+    }
+    return 0;
+}
+
+int klt_oracle_mask_from_points(const float* pts /* n x (x, y) */, int n, int radius, int w, int h, uint8_t* mask, int64_t pitch)
+{
+    if (n < 0 || radius < 0 || w < 1 || h < 1 || !mask || (n > 0 && !pts)) return -1;
+    int* half = (int*)malloc(sizeof(int) * (size_t)(radius + 1));
+    if (!half) return -2;
+    klt_oracle_circle_half_widths(radius, half);
+    for (int y = 0; y < h; ++y) memset(mask + (int64_t)y * pitch, 255, (size_t)w);
+    for (int i = 0; i < n; ++i) {
+        const int cx = (int)pts[2 * i], cy = (int)pts[2 * i + 1];      /* np.int32(): truncation toward zero */
+        for (int d = -radius; d <= radius; ++d) {
+            const int y = cy + d, hw = half[d < 0 ? -d : d];
+            if (y < 0 || y >= h || hw < 0) continue;
+            int x1 = cx - hw, x2 = cx + hw;
+            if (x1 < 0) x1 = 0;
+            if (x2 > w - 1) x2 = w - 1;
+            for (int x = x1; x <= x2; ++x) mask[(int64_t)y * pitch + x] = 0;
+        }
+    }
+    free(half);
+    return 0;
+}

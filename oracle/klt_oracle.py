@@ -52,6 +52,10 @@ def lib():
         L.klt_oracle_good_features_to_track.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int64, c.c_void_p, c.c_int64, c.c_int,
                                                         c.c_double, c.c_double, c.c_int, c.c_void_p, c.c_int]
         L.klt_oracle_good_features_to_track.restype = c.c_int
+        L.klt_oracle_circle_half_widths.argtypes = [c.c_int, c.c_void_p]
+        L.klt_oracle_circle_half_widths.restype = c.c_int
+        L.klt_oracle_mask_from_points.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64]
+        L.klt_oracle_mask_from_points.restype = c.c_int
         _lib = L
     return _lib
 
@@ -184,3 +188,15 @@ def good_features_to_track(img, max_corners, quality_level, min_distance, mask=N
     if n < 0:
         raise ValueError("oracle: good_features_to_track failed (%d)" % n)
     return out[:n].reshape(-1, 1, 2).copy() if n else None
+
+
+def mask_from_points(points, radius, shape):
+    """The detection mask of reference src/extractor/extractor.py:102-107: 255 everywhere, filled cv2.circle of `radius`
+    with value 0 around np.int32 of every point -> uint8 (h, w)."""
+    pts = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1, 2))
+    h, w = int(shape[0]), int(shape[1])
+    out = np.empty((h, w), np.uint8)
+    rc = lib().klt_oracle_mask_from_points(pts.ctypes.data if len(pts) else None, len(pts), int(radius), w, h, out.ctypes.data, w)
+    if rc < 0:
+        raise ValueError("oracle: mask_from_points failed (%d)" % rc)
+    return out

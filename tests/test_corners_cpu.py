@@ -154,3 +154,18 @@ def test_detection_has_no_cpu_fallback(klt):
         klt.goodFeaturesToTrack(img, 10, 0.01, 3.0)
     with pytest.raises(klt.KLTLibraryError):
         klt.cornerMinEigenVal(img, 3)
+
+
+@pytest.mark.parametrize("radius", [0, 1, 2, 3, 5, 7, 10, 16, 31, 50])
+def test_oracle_circle_mask_equals_cv2_circle(oracle, radius):
+    """Detection mask of extractor.py:102-107: np.int32 centres (inside, on and outside the border), filled cv2.circle."""
+    import cv2
+    rng = np.random.default_rng(radius)
+    for shape in [(60, 80), (37, 23), (200, 300)]:
+        h, w = shape
+        pts = np.stack([rng.uniform(-radius - 5, w + radius + 5, 60), rng.uniform(-radius - 5, h + radius + 5, 60)], -1).astype(np.float32)
+        want = np.zeros(shape, np.uint8)
+        want[:] = 255
+        for x, y in [np.int32(p) for p in pts.astype(np.float64)]:
+            cv2.circle(want, (int(x), int(y)), radius, 0, -1)
+        assert np.array_equal(oracle.mask_from_points(pts, radius, shape), want)

@@ -239,3 +239,35 @@ def test_eigenvalue_map_properties_at_full_size(klt):
     assert scale > 0 and np.abs(e - ef).max() <= 1e-5 * scale          # tolerance: float32 sums in a different order
     assert e.min() >= -1e-6 * scale
     assert not klt.cornerMinEigenVal(np.full((2160, 3840), 200, np.uint8), 31).any()
+
+
+@pytest.mark.parametrize("radius", [0, 1, 5, 10, 31, 100])
+def test_device_mask_from_points_equals_cv2_circle(klt, cv2, oracle, radius):
+    import torch
+    from visual_odom_pipeline_b200 import detector as D
+    rng = np.random.default_rng(radius + 1)
+    for shape in [(376, 1241), (61, 47)]:
+        h, w = shape
+        pts = np.stack([rng.uniform(-radius - 5, w + radius + 5, 300), rng.uniform(-radius - 5, h + radius + 5, 300)], -1).astype(np.float32)
+        want = np.zeros(shape, np.uint8)
+        want[:] = 255
+        for x, y in [np.int32(p) for p in pts.astype(np.float64)]:
+            cv2.circle(want, (int(x), int(y)), radius, 0, -1)
+        got = D.mask_from_points(torch.from_numpy(pts).cuda(), radius, shape).cpu().numpy()
+        assert np.array_equal(got, want) and np.array_equal(got, oracle.mask_from_points(pts, radius, shape))
+    assert np.array_equal(D.mask_from_points(torch.zeros((0, 2), dtype=torch.float32, device="cuda"), 5, (20, 30)).cpu().numpy(),
+                          np.full((20, 30), 255, np.uint8))
+
+
+def test_fused_detection_from_tracked_points_equals_reference_step(klt, cv2):
+    """detectNewFeatures(image, tracked, mask_radius) == the mask loop + cv2.goodFeaturesToTrack of extractor.py:102-111."""
+    for hw, n_tracked, seed in [((376, 1241), 1500, 3), ((768, 1024), 3000, 4), ((120, 160), 0, 5)]:
+        img = S.frame_pair(hw[0], hw[1], seed=seed)[0]
+        tracked = S.uniform_points(max(n_tracked, 1), hw[0], hw[1], seed=seed + 1, margin=15).reshape(-1, 2)[:n_tracked]
+        mask = np.zeros_like(img)
+        mask[:] = 255
+        for x, y in [np.int32(p) for p in tracked.astype(np.float64)]:
+            cv2.circle(mask, (int(x), int(y)), 10, 0, -1)
+        want = cv2.goodFeaturesToTrack(img, mask=mask, maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)
+        got = klt.detectNewFeatures(img, tracked, 10)
+        assert same(got, want), hw

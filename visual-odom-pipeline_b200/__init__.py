@@ -6,10 +6,10 @@ Import name: ``visual_odom_pipeline_b200`` (the on-disk directory is ``visual-od
 """
 from ._lib import (KLTLibraryError, LIB_PATH, OPTFLOW_LK_GET_MIN_EIGENVALS, OPTFLOW_USE_INITIAL_FLOW, TERM_COUNT,
                    TERM_EPS, Context, default_context)
-from .corners import cornerMinEigenVal, goodFeaturesToTrack
+from .corners import cornerMinEigenVal, detectNewFeatures, goodFeaturesToTrack
 from .lk import buildOpticalFlowPyramid, calcOpticalFlowPyrLK, error, pinned_empty, trackBidirectional
 
-__all__ = ["calcOpticalFlowPyrLK", "buildOpticalFlowPyramid", "trackBidirectional", "goodFeaturesToTrack", "cornerMinEigenVal", "error", "pinned_empty", "Context", "default_context",
+__all__ = ["calcOpticalFlowPyrLK", "buildOpticalFlowPyramid", "trackBidirectional", "goodFeaturesToTrack", "cornerMinEigenVal", "detectNewFeatures", "error", "pinned_empty", "Context", "default_context",
            "KLTLibraryError", "LIB_PATH", "TERM_COUNT", "TERM_EPS", "OPTFLOW_USE_INITIAL_FLOW",
            "OPTFLOW_LK_GET_MIN_EIGENVALS"]
 __version__ = "0.1.1"

@@ -65,6 +65,9 @@ SYMBOLS = {
     "klt_corner_min_eigen_val_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _P]),
     "klt_good_features_to_track_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int64, _c.c_int, _c.c_double,
                                                    _c.c_double, _c.c_int, _P, _c.c_int, _c.POINTER(_c.c_int)]),
+    "klt_good_features_to_track_points_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _c.c_int,
+                                                          _c.c_double, _c.c_double, _c.c_int, _P, _c.c_int, _c.POINTER(_c.c_int)]),
+    "klt_corner_mask_from_points": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int64, _P]),
 }
 
 _lib = None

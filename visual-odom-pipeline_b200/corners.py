@@ -97,3 +97,39 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=No
     if n.value == 0:
         return None
     return out[:n.value].reshape(-1, 1, 2).copy() if n.value < cap else out.reshape(-1, 1, 2)
+
+
+def detectNewFeatures(image, trackedPoints, maskRadius, maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31,
+                      device=0):
+    """The detection step of the reference's ``Extractor.extract(..., detector='shi-tomasi')`` fused into one call
+    (src/extractor/extractor.py:102-111; opt-in, like trackBidirectional for the tracking step):
+
+        mask = 255; for (x, y) in np.int32(tracked): cv2.circle(mask, (x, y), maskRadius, 0, -1)
+        return cv2.goodFeaturesToTrack(image, mask=mask, maxCorners=..., qualityLevel=..., minDistance=..., blockSize=...)
+
+    The mask is rasterised on the device from the tracked keypoints (float32 (N, 2) / (N, 1, 2); 8 bytes per point go up
+    instead of a w x h mask, and the Python loop over cv2.circle disappears).  Same corners, same order as the two cv2
+    calls.  Defaults are the reference's parameters (extractor.py:21-24)."""
+    img = _u8_image(image, "image", "goodFeaturesToTrack")
+    h, w = img.shape
+    maxCorners, blockSize, maskRadius = int(maxCorners), int(blockSize), int(maskRadius)
+    qualityLevel, minDistance = float(qualityLevel), float(minDistance)
+    if not (qualityLevel > 0 and minDistance >= 0 and maxCorners >= 0):
+        _fail("qualityLevel > 0 && minDistance >= 0 && maxCorners >= 0 in function 'goodFeaturesToTrack'")
+    if blockSize < 1 or maskRadius < 0:
+        _fail("blockSize > 0 && radius >= 0")
+    pts = np.zeros((0, 2), np.float32) if trackedPoints is None else np.ascontiguousarray(np.asarray(trackedPoints, np.float32).reshape(-1, 2))
+    cap = maxCorners if maxCorners > 0 else w * h
+    out = np.empty((cap, 2), np.float32)
+    n = ctypes.c_int(0)
+    ctx = _lib.default_context(device)
+    with ctx.lock:
+        rc = _lib.load().klt_good_features_to_track_points_host(ctx.handle, img.ctypes.data, img.strides[0], w, h,
+                                                                pts.ctypes.data if len(pts) else None, len(pts), maskRadius,
+                                                                maxCorners, qualityLevel, minDistance, blockSize,
+                                                                out.ctypes.data, cap, ctypes.byref(n))
+    if rc != KLT_OK:
+        _raise_status(rc, "detectNewFeatures")
+    if n.value == 0:
+        return None
+    return out[:n.value].reshape(-1, 1, 2).copy() if n.value < cap else out.reshape(-1, 1, 2)

@@ -704,10 +704,15 @@ klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64
     return KLT_OK;
 }
 
-klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
-                                           const uint8_t* mask, int64_t mask_pitch, int max_corners, double quality_level,
-                                           double min_distance, int block_size, float* corners, int capacity, int* n_out)
+// mask given by the caller (host image) or rasterised on the device from `points` (n_points >= 0 with mask == NULL and
+// mask_radius >= 0: extractor.py:102-107)
+static klt_status gftt_host_impl(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                                 const uint8_t* mask, int64_t mask_pitch, const float* points, int n_points, int mask_radius,
+                                 int max_corners, double quality_level,
+                                 double min_distance, int block_size, float* corners, int capacity, int* n_out)
 {
+    const bool from_points = mask_radius >= 0;
+    if (from_points && (mask || n_points < 0 || (n_points > 0 && !points) || mask_radius > 127)) return mask_radius > 127 ? KLT_ERR_UNSUPPORTED : KLT_ERR_INVALID_ARG;
     if (!ctx || !img || !n_out || w < 1 || h < 1 || pitch < w || block_size < 1 || capacity < 0 || (capacity > 0 && !corners))
         return KLT_ERR_INVALID_ARG;
     if (!(quality_level > 0) || !(min_distance >= 0) || max_corners < 0) return KLT_ERR_INVALID_ARG;   // CV_Assert of goodFeaturesToTrack
@@ -716,7 +721,8 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
     *n_out = 0;
     KLT_CUDA(cudaSetDevice(ctx->device));
     const size_t img_bytes = upload_bytes(pitch, w, h);
-    const size_t mask_bytes = mask ? upload_bytes(mask_pitch, w, h) : 0;
+    const size_t pts_bytes = from_points ? align_up((size_t)n_points * 8 + 8, 256) : 0;
+    const size_t mask_bytes = mask ? upload_bytes(mask_pitch, w, h) : (from_points ? align_up((size_t)w * h, 256) + pts_bytes : 0);
     const size_t eig_bytes = align_up((size_t)w * h * 4, 256);
     const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
     // up to direct_cap sorted candidate keys land directly in the context's page-locked, device-mapped staging buffer
@@ -738,11 +744,19 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
         s = upload_u8(d + off_mask, &mpitch, mask, mask_pitch, w, h, st2);
         if (s != KLT_OK) return s;
         KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
+    } else if (from_points) {
+        // tracked keypoints up (8 bytes each), discs rasterised on the device while the image is still in flight
+        float* d_pts = reinterpret_cast<float*>(d + off_mask + align_up((size_t)w * h, 256));
+        if (n_points > 0) KLT_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)n_points * 8, cudaMemcpyHostToDevice, st2));
+        mpitch = w;
+        s = corner_mask_from_points_launch(d_pts, n_points, mask_radius, w, h, d + off_mask, mpitch, st2);
+        if (s != KLT_OK) return s;
+        KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
     }
     s = upload_u8(d + off_img, &ipitch, img, pitch, w, h, st);
     if (s != KLT_OK) return s;
-    if (mask) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
-    const uint8_t* d_mask = mask ? d + off_mask : nullptr;
+    if (mask || from_points) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
+    const uint8_t* d_mask = (mask || from_points) ? d + off_mask : nullptr;
     float* d_eig = reinterpret_cast<float*>(d + off_eig);
     static const bool trace = getenv("KLT_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -816,6 +830,31 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
         std::fprintf(stderr, "[klt trace] gftt: h2d done +%.1f us, eigenvalue kernels +%.1f us, candidates + sort + sync +%.1f us (%u candidates), host sort + selection %.1f us\n",
                      us(t0, t1), us(t1, t2), us(t2, t3), count, us(t3, now()));
     return s;
+}
+
+klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                                           const uint8_t* mask, int64_t mask_pitch, int max_corners, double quality_level,
+                                           double min_distance, int block_size, float* corners, int capacity, int* n_out)
+{
+    return gftt_host_impl(ctx, img, pitch, w, h, mask, mask_pitch, nullptr, 0, -1, max_corners, quality_level, min_distance, block_size,
+                          corners, capacity, n_out);
+}
+
+klt_status klt_good_features_to_track_points_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
+                                                  const float* points, int n_points, int mask_radius, int max_corners,
+                                                  double quality_level, double min_distance, int block_size, float* corners,
+                                                  int capacity, int* n_out)
+{
+    if (mask_radius < 0) return KLT_ERR_INVALID_ARG;
+    return gftt_host_impl(ctx, img, pitch, w, h, nullptr, 0, points, n_points, mask_radius, max_corners, quality_level, min_distance,
+                          block_size, corners, capacity, n_out);
+}
+
+klt_status klt_corner_mask_from_points(klt_ctx* ctx, const float* d_points, int n, int radius, int w, int h, uint8_t* d_mask,
+                                       int64_t mask_pitch, void* stream)
+{
+    if (!ctx) return KLT_ERR_INVALID_ARG;
+    return corner_mask_from_points_launch(d_points, n, radius, w, h, d_mask, mask_pitch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

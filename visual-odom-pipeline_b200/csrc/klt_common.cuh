@@ -95,6 +95,9 @@ klt_status corner_candidates_launch(const float* eig, long long eig_pitch, long 
 klt_status corner_sort_launch(const unsigned long long* keys, long long keys_batch_stride, const unsigned* count, int batch,
                               unsigned* rank, unsigned long long* out, long long out_batch_stride, int out_capacity,
                               cudaStream_t stream);
+// 255 everywhere, filled cv2.circle(radius) of 0 around np.int32 of every point (reference extractor.py:102-107)
+klt_status corner_mask_from_points_launch(const float* pts, int n, int radius, int w, int h, uint8_t* mask, long long pitch,
+                                          cudaStream_t stream);
 // greedy minimum-distance selection on the device (one block per image) from the sorted list of corner_sort_launch;
 // out[0] = bit 63 (done here) | corner count, or the candidate count with bit 63 clear (host has to do it), corners as
 // float2 from out[1]

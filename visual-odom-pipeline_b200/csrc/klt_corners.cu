@@ -714,6 +714,40 @@ select_corners_kernel(const unsigned long long* __restrict__ sorted, long long s
     if (tid == 0) dst[0] = (1ull << 63) | (unsigned long long)(unsigned)accepted_total;   // bit 63: selection done here
 }
 
+// ---- mask_from_points_kernel ----------------------------------------------------------------------------------
+// The detection mask of reference src/extractor/extractor.py:102-107 on the device: 255 everywhere, then a filled
+// cv2.circle of value 0 around np.int32(x, y) of every tracked keypoint.  OpenCV's filled circle is the midpoint circle:
+// row cy +- d is filled over [cx - half[d], cx + half[d]] (table computed by the launcher with OpenCV's octant walk).
+struct CircleTable { short half[128]; };
+
+__global__ void __launch_bounds__(256)
+mask_fill_kernel(uint8_t* __restrict__ mask, long long pitch, int w, int h)
+{
+    const int x = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= w) return;
+    uint8_t* p = mask + (long long)y * pitch + x;
+    if (x + 3 < w && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) *reinterpret_cast<unsigned*>(p) = 0xffffffffu;
+    else for (int i = 0; i < 4 && x + i < w; ++i) p[i] = 255;
+}
+
+__global__ void __launch_bounds__(256)
+mask_from_points_kernel(const float* __restrict__ pts, int n, int radius, int w, int h, uint8_t* __restrict__ mask, long long pitch,
+                        const __grid_constant__ CircleTable tab)
+{
+    const int rows_per = 2 * radius + 1;
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)n * rows_per) return;
+    const int i = (int)(t / rows_per), d = (int)(t - (long long)i * rows_per) - radius;
+    const float fx = pts[2 * i], fy = pts[2 * i + 1];
+    if (!(fabsf(fx) < 1.0e9f) || !(fabsf(fy) < 1.0e9f)) return;         // NaN / out of int range: np.int32 is undefined there
+    const int cx = (int)fx, cy = (int)fy;                                 // truncation toward zero, like np.int32
+    const int y = cy + d, hw = tab.half[d < 0 ? -d : d];
+    if (y < 0 || y >= h || hw < 0) return;
+    const int x1 = max(cx - hw, 0), x2 = min(cx + hw, w - 1);
+    uint8_t* __restrict__ row = mask + (long long)y * pitch;
+    for (int x = x1; x <= x2; ++x) row[x] = 0;
+}
+
 }  // namespace
 
 long long corners_ws_bytes(int w, int h, int batch)
@@ -806,6 +840,37 @@ klt_status corner_select_launch(const unsigned long long* sorted, long long sort
     }
     select_corners_kernel<<<batch, kSelThreads, smem, stream>>>(sorted, sorted_batch_stride, w, h, md2, radius, max_corners, out,
                                                                  out_batch_stride, out_capacity);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+klt_status corner_mask_from_points_launch(const float* pts, int n, int radius, int w, int h, uint8_t* mask, long long pitch,
+                                          cudaStream_t stream)
+{
+    if (n < 0 || radius < 0 || w < 1 || h < 1 || !mask || pitch < w || (n > 0 && !pts)) return KLT_ERR_INVALID_ARG;
+    if (radius > 127 || h > 65535) return KLT_ERR_UNSUPPORTED;
+    CircleTable tab;
+    for (int i = 0; i < 128; ++i) tab.half[i] = -1;
+    {   // OpenCV's Circle() octant walk (drawing.cpp): rows cy -+ dy get [cx - dx, cx + dx], rows cy -+ dx get [cx - dy, cx + dy]
+        int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+        while (dx >= dy) {
+            if (dx > tab.half[dy]) tab.half[dy] = (short)dx;
+            if (dy > tab.half[dx]) tab.half[dx] = (short)dy;
+            dy++;
+            err += plus;
+            plus += 2;
+            const int m = (err <= 0) - 1;
+            err -= minus & m;
+            dx += m;
+            minus -= m & 2;
+        }
+    }
+    mask_fill_kernel<<<dim3((w + 1023) / 1024, h), 256, 0, stream>>>(mask, pitch, w, h);
+    const long long total = (long long)n * (2 * radius + 1);
+    if (total > 0) {
+        if ((total + 255) / 256 > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+        mask_from_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pts, n, radius, w, h, mask, pitch, tab);
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }

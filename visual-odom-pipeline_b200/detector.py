@@ -84,3 +84,20 @@ def good_features_to_track(images, maxCorners, qualityLevel, minDistance, mask=N
             _raise_status(rc, "klt_select_corners_host")
         out.append(res[:n.value].reshape(-1, 1, 2).copy() if n.value else None)
     return out
+
+
+def mask_from_points(points, radius, shape, ctx=None):
+    """Detection mask of reference src/extractor/extractor.py:102-107 for (N, 2) float32 CUDA points -> (H, W) uint8 CUDA
+    tensor: 255, with a filled cv2.circle of `radius` (value 0) around np.int32 of every point."""
+    torch = _torch()
+    if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float32):
+        raise error("klt_b200: points must be a float32 CUDA tensor")
+    pts = points.reshape(-1, 2).contiguous()
+    h, w = int(shape[0]), int(shape[1])
+    mask = torch.empty((h, w), dtype=torch.uint8, device=pts.device)
+    ctx = ctx or _lib.default_context(pts.device.index or 0)
+    rc = _lib.load().klt_corner_mask_from_points(ctx.handle, pts.data_ptr() if pts.numel() else None, pts.shape[0], int(radius), w, h,
+                                                 mask.data_ptr(), w, _stream_ptr(mask))
+    if rc != KLT_OK:
+        _raise_status(rc, "klt_corner_mask_from_points")
+    return mask
