@@ -271,3 +271,37 @@ def test_fused_detection_from_tracked_points_equals_reference_step(klt, cv2):
         want = cv2.goodFeaturesToTrack(img, mask=mask, maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)
         got = klt.detectNewFeatures(img, tracked, 10)
         assert same(got, want), hw
+
+
+def test_device_resident_frame_step_equals_cv2_loop(klt, cv2):
+    """KLTTracker.step(): tracking + filtering + mask + detection of one frame on the device == the same steps with cv2
+    (the reference's extend_tracks / extract sequence, src/extractor/extractor.py:38-59,102-111)."""
+    import torch
+    from visual_odom_pipeline_b200 import tracker as T
+    lk_params = dict(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+    st_params = dict(maxCorners=1000, qualityLevel=0.03, minDistance=10, blockSize=31)
+    frames = S.sequence(376, 1241, 4, seed=14)
+    h, w = frames[0].shape
+    pts = cv2.goodFeaturesToTrack(frames[0], **st_params).reshape(-1, 2)
+    trk = T.KLTTracker(**lk_params).reset(torch.from_numpy(frames[0]).cuda())
+    dpts = torch.from_numpy(pts).cuda()
+    for t in range(1, len(frames)):
+        im0, im1 = frames[t - 1], frames[t]
+        p0 = pts.reshape(-1, 1, 2)
+        p1, _s, _e = cv2.calcOpticalFlowPyrLK(im0, im1, p0, None, **lk_params)
+        p0r, _s, _e = cv2.calcOpticalFlowPyrLK(im0, im1, p1, None, **lk_params)
+        good = abs(p0 - p0r).reshape(-1, 2).max(-1) < 30
+        p1 = p1.reshape(-1, 2)
+        keep_ref = good & (0 <= p1[:, 0]) & (p1[:, 0] <= w) & (0 <= p1[:, 1]) & (p1[:, 1] <= h)
+        surv_ref = p1[keep_ref]
+        mask = np.zeros_like(im1)
+        mask[:] = 255
+        for x, y in [np.int32(p) for p in surv_ref]:
+            cv2.circle(mask, (int(x), int(y)), 10, 0, -1)
+        new_ref = cv2.goodFeaturesToTrack(im1, mask=mask, **st_params)
+        surv, keep, new = trk.step(torch.from_numpy(im1).cuda(), dpts)
+        assert np.array_equal(keep.cpu().numpy(), keep_ref), "frame %d" % t
+        assert np.array_equal(surv.cpu().numpy().view(np.uint32), surv_ref.view(np.uint32)), "frame %d" % t
+        assert same(new, new_ref), "frame %d" % t
+        pts = surv_ref if new_ref is None else np.concatenate([surv_ref, new_ref.reshape(-1, 2)])
+        dpts = torch.from_numpy(np.ascontiguousarray(pts)).cuda()

@@ -222,3 +222,32 @@ class KLTTracker:
         H, W = self.prev.images.shape[1], self.prev.images.shape[2]
         keep, bidir = track_filter(prevPts, p1, p0r, max_bidir_error, W, H, ctx=self.prev.ctx)
         return p1, keep, bidir, st, er
+
+    def step(self, image, points, max_bidir_error=30, mask_radius=10, maxCorners=1000, qualityLevel=0.03, minDistance=10,
+             blockSize=31):
+        """One frame of the reference's data-parallel work for ONE sequence, everything on the device
+        (src/pipeline/pipeline.py:98-103,159-163 with src/extractor/extractor.py:38-88,102-111): track `points`
+        (N, 2) float32 CUDA tensor from the stored frame into `image` (forward pass + the reference's second pass),
+        drop them by bidirectional error and the inclusive bounds test, rasterise the detection mask around the
+        survivors, detect new Shi-Tomasi corners.  One upload (the new frame, by the caller) and one small download
+        (candidate keys for the sequential selection) per frame.
+        -> survivors (M, 2) float32 CUDA, keep (N,) bool CUDA, new corners float32 (K, 1, 2) numpy or None"""
+        torch = _torch()
+        from . import detector as D
+        img = _as_image_batch(image)
+        if img.shape[0] != 1:
+            raise error("klt_b200: KLTTracker.step() takes one frame")
+        pts = points.reshape(1, -1, 2)
+        if pts.shape[1]:
+            p1, keep, _bidir, _st, _er = self.track_filtered(img, pts, max_bidir_error)
+            survivors = p1[0][keep[0]]
+            keep = keep[0]
+        else:
+            self.prev = DevicePyramid(img, self.winSize, self.maxLevel, ctx=self.prev.ctx if self.prev is not None else None)
+            survivors = torch.zeros((0, 2), dtype=torch.float32, device=img.device)
+            keep = torch.zeros((0,), dtype=torch.bool, device=img.device)
+        H, W = img.shape[1], img.shape[2]
+        mask = D.mask_from_points(survivors, mask_radius, (H, W), ctx=self.prev.ctx)
+        new = D.good_features_to_track(img, maxCorners, qualityLevel, minDistance, mask=mask.unsqueeze(0), blockSize=blockSize,
+                                       ctx=self.prev.ctx)[0]
+        return survivors, keep, new
