@@ -457,6 +457,51 @@ def main():
             for r_ in range(dreps):
                 K.detectNewFeatures(dimgs[r_ % n_host], tracked, 10, device=local_rank, **det_kw)
             det_pts_ms = 1e3 * (time.perf_counter() - t0) / dreps
+            # the whole data-parallel part of a frame chained on the device (KLTTracker.step: forward + second LK pass with
+            # the reference's parameters, filter, mask, detection) against the same sequence of cv2 calls
+            frame_step = None
+            try:
+                import cv2
+                from visual_odom_pipeline_b200 import synth as S2, tracker as T2
+                lkp = dict(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))      # extractor.py:16-19
+                seq = S2.sequence(h, w, 6, seed=11)
+                dseq = [torch.from_numpy(f).to(dev) for f in seq]
+                p_init = hp[0][2].reshape(-1, 2).copy()
+                def run_b200(reps):
+                    trk = T2.KLTTracker(**lkp).reset(dseq[0])
+                    pts_d = torch.from_numpy(p_init).to(dev)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for r_ in range(reps):
+                        surv, keep_, new_ = trk.step(dseq[1 + r_ % 5], pts_d)
+                    torch.cuda.synchronize()
+                    return (time.perf_counter() - t0) / reps, int(surv.shape[0]), 0 if new_ is None else len(new_)
+                run_b200(5)
+                fs_ms, n_surv, n_new = run_b200(50)
+                def run_cv2(reps):
+                    t0 = time.perf_counter()
+                    for r_ in range(reps):
+                        im0, im1 = seq[0], seq[1 + r_ % 5]
+                        p0 = p_init.reshape(-1, 1, 2)
+                        p1, _a, _b = cv2.calcOpticalFlowPyrLK(im0, im1, p0, None, **lkp)
+                        p0r, _a, _b = cv2.calcOpticalFlowPyrLK(im0, im1, p1, None, **lkp)
+                        good = abs(p0 - p0r).reshape(-1, 2).max(-1) < 30
+                        q = p1.reshape(-1, 2)
+                        kp_ = q[good & (0 <= q[:, 0]) & (q[:, 0] <= w) & (0 <= q[:, 1]) & (q[:, 1] <= h)]
+                        m_ = np.zeros_like(im1)
+                        m_[:] = 255
+                        for x_, y_ in [np.int32(p_) for p_ in kp_]:
+                            cv2.circle(m_, (int(x_), int(y_)), 10, 0, -1)
+                        cv2.goodFeaturesToTrack(im1, mask=m_, **det_kw)
+                    return (time.perf_counter() - t0) / reps
+                frame_step = {"api": "KLTTracker.step(frame, points): 2 LK passes (win 31, eps 0.03), filter, mask, goodFeaturesToTrack; frames and points device-resident",
+                              "ms_per_frame": 1e3 * fs_ms, "tracked": int(len(p_init)), "survivors": n_surv, "new_corners": n_new}
+                if world == 1 and not args.no_cpu_baseline:
+                    run_cv2(2)
+                    frame_step["cv2_ms_per_frame"] = 1e3 * run_cv2(10)
+                    frame_step["cv2_note"] = "same steps with cv2 on the host (%d threads), incl. the reference's Python loop over cv2.circle" % cv2.getNumThreads()
+            except Exception as ex:   # pragma: no cover
+                frame_step = {"error": repr(ex)}
             # device-resident, batched eigenvalue maps (the kernels only): 64 frames per launch sequence
             nbd = min(64, 2 * P)
             de = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -470,6 +515,7 @@ def main():
             detection = {"api": "visual_odom_pipeline_b200.goodFeaturesToTrack(numpy pinned image, mask, %s) -> numpy" % det_kw,
                          "e2e_ms_per_frame": det_ms, "frames_per_sec": 1e3 / det_ms, "corners": 0 if got is None else int(len(got)),
                          "h2d_bytes_per_frame": 2 * w * h,
+                         "frame_step": frame_step,
                          "fused_from_tracked_points": {"api": "visual_odom_pipeline_b200.detectNewFeatures(image, %d tracked keypoints, mask_radius=10)" % n,
                                                        "e2e_ms_per_frame": det_pts_ms, "h2d_bytes_per_frame": w * h + 8 * n,
                                                        "note": "mask of extractor.py:102-107 rasterised on the device; the reference additionally spends "
