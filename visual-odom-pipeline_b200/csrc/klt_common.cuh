@@ -35,6 +35,20 @@ __host__ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must opt each of them in to the large
+// dynamic shared memory of a kernel.  Returns true when the current device still needs it for this call site.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool needed()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown: just set it again
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // u / d for small operands via a 12.20 reciprocal: exact for u < 4096, 1 <= d <= 64
 // (u*magic < 2^32 and the rounding excess u*e/2^20 stays below 1/d).
 __host__ __device__ __forceinline__ unsigned fastdiv_magic(unsigned d) { return ((1u << 20) + d - 1u) / d; }

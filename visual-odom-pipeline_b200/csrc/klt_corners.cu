@@ -772,12 +772,11 @@ klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long 
     const float k0 = (float)(2.0 / (4.0 * (double)block * 255.0));
     cov_kernel<<<dim3((w + kTile - 1) / kTile, (h + kTile - 1) / kTile, batch), dim3(32, 8), 0, stream>>>(
         img, pitch, batch_stride, w, h, covT, hp, k1, k0);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed()) {
         cudaError_t ce = cudaFuncSetAttribute(row_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowSmem));
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(col_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColSmem));
         if (ce != cudaSuccess) return (klt_status)ce;
-        configured = true;
     }
     if (block == 3 || block == 5)
         row_sum_small_kernel<<<dim3((h + 31) / 32, (w + 7) / 8, 3 * batch), dim3(32, 8), 0, stream>>>(covT, w, h, hp, block, rows, wd);
@@ -809,11 +808,10 @@ klt_status corner_sort_launch(const unsigned long long* keys, long long keys_bat
 {
     if (batch < 1 || batch > 65535 || out_capacity < 0) return KLT_ERR_INVALID_ARG;
     // rank: batch * 8192 words, zeroed by the caller
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed()) {
         cudaError_t ce = cudaFuncSetAttribute(scatter_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * 8);
         if (ce != cudaSuccess) return (klt_status)ce;
-        configured = true;
     }
     rank_keys_kernel<<<dim3(kSortMax / kRankI, kSortMax / kRankJ, batch), kRankI / 2, 0, stream>>>(keys, keys_batch_stride, count, rank);
     scatter_keys_kernel<<<batch, 1024, kSortMax * 8, stream>>>(keys, keys_batch_stride, count, rank, out, out_batch_stride, out_capacity);
@@ -832,11 +830,10 @@ klt_status corner_select_launch(const unsigned long long* sorted, long long sort
     while (radius <= kSelMaxRadius && (long long)(radius + 1) * (radius + 1) < md2) ++radius;   // largest r with r^2 < md2 (or > table)
     const long long nwords = (long long)((w + 31) / 32) * h;
     const size_t smem = nwords <= kSelMaxBitmapWords ? (size_t)nwords * 4 : 0;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed()) {
         cudaError_t ce = cudaFuncSetAttribute(select_corners_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxBitmapWords * 4);
         if (ce != cudaSuccess) return (klt_status)ce;
-        configured = true;
     }
     select_corners_kernel<<<batch, kSelThreads, smem, stream>>>(sorted, sorted_batch_stride, w, h, md2, radius, max_corners, out,
                                                                  out_batch_stride, out_capacity);

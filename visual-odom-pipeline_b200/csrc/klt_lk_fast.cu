@@ -845,12 +845,11 @@ klt_status launch_fast(const LKLaunch& L, cudaStream_t stream)
     using C = Cfg<WW, WH, WPP>;
     static_assert(WW * WH <= 2056, "err pass assumes an exact float32 sum");
     static_assert(C::UPT <= 8, "per-thread bound accumulators would overflow");
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const size_t smem = (size_t)C::POINT_BYTES * C::PPC;
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(lk_fast_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (klt_status)e;
-        configured = true;
     }
     const long long total = (long long)L.n_per_pair * L.batch;
     const long long blocks = (total + C::PPC - 1) / C::PPC;

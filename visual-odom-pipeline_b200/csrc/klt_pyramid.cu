@@ -700,12 +700,11 @@ EncodeTiledFn encode_tiled_fn()
 klt_status launch_tma(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
                       int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
 {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const int smem = kTmaWarpBytes * kWarpsPerBlock;
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(pyr_down_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
-        configured = true;
     }
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return KLT_ERR_INTERNAL;
@@ -750,12 +749,11 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
                        int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count, cudaStream_t stream)
 {
     using RC = RingCfg<8>;
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const int smem = RC::WARP_BYTES * kWarpsPerBlock;
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(pyr_down_ring_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
-        configured = true;
     }
     const int n8 = w / RC::BODY, rem = w - n8 * RC::BODY;
     const int rem_nout = (rem == 0) ? 0 : (rem <= RingCfg<4>::BODY ? 4 : 8);
