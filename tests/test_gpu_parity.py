@@ -351,3 +351,19 @@ print("fused pyramid ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, KLT_PYR_FUSE="1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fused pyramid ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_second_device_in_the_same_process(klt, cv2):
+    """One process driving two GPUs (a context per device): the kernels' dynamic shared-memory opt-in is per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a, b = S.frame_pair(376, 1241, seed=8)
+    p = S.uniform_points(500, 376, 1241, seed=9)
+    lk = dict(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03))
+    ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, **lk)
+    refc = cv2.goodFeaturesToTrack(a, 1000, 0.03, 10, blockSize=31)
+    for dev in (0, 1, 0, 1):
+        assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, device=dev, **lk), ref, "device %d" % dev)
+        got = klt.goodFeaturesToTrack(a, 1000, 0.03, 10, blockSize=31, device=dev)
+        assert got.shape == refc.shape and np.array_equal(got, refc)
