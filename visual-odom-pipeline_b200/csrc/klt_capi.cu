@@ -613,6 +613,53 @@ static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, in
         const int cell = (int)std::lrint(min_distance);
         const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
         const double md2 = min_distance * min_distance;
+        const double md2c = std::ceil(md2);   // squared pixel distances are integers: d2 < md2  <=>  d2 < ceil(md2)
+        const long long md2i = md2c < 9.0e18 ? (long long)md2c : (long long)9.0e18;
+        // x / cell for 16-bit x by multiplication: exact since x * (cell - 1) < 2^32
+        const uint64_t magic = cell > 1 ? ((1ull << 32) + (uint64_t)cell - 1) / (uint64_t)cell : 0;
+        if ((size_t)(gw + 2) * (gh + 2) <= (1u << 20)) {
+            // Fast path: a padded grid (no clamping) of per-cell counters and up to 4 inline corners per cell -- accepted
+            // corners are >= minDistance apart and a cell is at most minDistance + 0.5 wide, so 4 is never exceeded (checked).
+            // A candidate first reads the 3 x 3 counters (three 3-byte reads); most candidates have empty neighbourhoods
+            // late in the list or find their conflict in the first occupied cell.
+            struct Cell { short x[4], y[4]; };
+            const int gw2 = gw + 2;
+            const size_t ncell = (size_t)gw2 * (gh + 2);
+            thread_local std::vector<unsigned char> cnt_buf;
+            thread_local std::vector<Cell> cell_buf;
+            try {
+                cnt_buf.assign(ncell + 4, 0);
+                if (cell_buf.size() < ncell) cell_buf.resize(ncell);
+            } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+            unsigned char* cnt = cnt_buf.data();
+            Cell* cells = cell_buf.data();
+            for (int64_t i = 0; i < n_keys; ++i) {
+                const int x = (int)(keys[i] & 0xffffu), y = (int)((keys[i] >> 16) & 0xffffu);
+                if (y >= h || x >= w) return KLT_ERR_INVALID_ARG;
+                const int xc = cell > 1 ? (int)(((uint64_t)x * magic) >> 32) : x, yc = cell > 1 ? (int)(((uint64_t)y * magic) >> 32) : y;
+                const size_t c0 = (size_t)yc * gw2 + xc;            // padded index of cell (yc - 1, xc - 1)
+                bool good = true;
+                for (int ry = 0; ry < 3 && good; ++ry) {
+                    const size_t row = c0 + (size_t)ry * gw2;
+                    if (!(cnt[row] | cnt[row + 1] | cnt[row + 2])) continue;
+                    for (int rx = 0; rx < 3 && good; ++rx) {
+                        const int m = cnt[row + rx];
+                        const Cell& cl = cells[row + rx];
+                        for (int j = 0; j < m; ++j) {
+                            const long long dx = x - cl.x[j], dy = y - cl.y[j];
+                            if (dx * dx + dy * dy < md2i) { good = false; break; }
+                        }
+                    }
+                }
+                if (!good) continue;
+                const size_t cc = c0 + gw2 + 1;
+                if (cnt[cc] >= 4) return KLT_ERR_INTERNAL;
+                cells[cc].x[cnt[cc]] = (short)x; cells[cc].y[cnt[cc]] = (short)y; ++cnt[cc];
+                if (emit(x, y)) break;
+            }
+            *n_out = nc;
+            return KLT_OK;
+        }
         // accepted corners: per-cell singly linked lists in flat arrays (scratch kept per thread across calls)
         const size_t max_acc = (size_t)((max_corners > 0 && max_corners < n_keys) ? max_corners : n_keys);
         thread_local std::vector<int> scratch;
@@ -625,10 +672,6 @@ static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, in
         int* ay = ax + max_acc;
         std::fill(head, head + (size_t)gw * gh, -1);
         int nacc = 0;
-        const double md2c = std::ceil(md2);   // squared pixel distances are integers: d2 < md2  <=>  d2 < ceil(md2)
-        const long long md2i = md2c < 9.0e18 ? (long long)md2c : (long long)9.0e18;
-        // x / cell for 16-bit x by multiplication: exact since x * (cell - 1) < 2^32
-        const uint64_t magic = cell > 1 ? ((1ull << 32) + (uint64_t)cell - 1) / (uint64_t)cell : 0;
         for (int64_t i = 0; i < n_keys; ++i) {
             const int x = (int)(keys[i] & 0xffffu), y = (int)((keys[i] >> 16) & 0xffffu);
             if (y >= h || x >= w) return KLT_ERR_INVALID_ARG;
