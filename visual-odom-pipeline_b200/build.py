@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libklt_b200.so")
-SOURCES = ["klt_pyramid.cu", "klt_lk.cu", "klt_lk_fast.cu", "klt_filter.cu", "klt_corners.cu", "klt_capi.cu"]
+SOURCES = ["klt_pyramid.cu", "klt_lk.cu", "klt_lk_fast.cu", "klt_lk_warp.cu", "klt_filter.cu", "klt_corners.cu", "klt_capi.cu"]
 HEADERS = [os.path.join(CSRC, "klt_common.cuh"), os.path.join(ROOT, "include", "klt_b200.h")]
 
 NVCC_FLAGS = [
@@ -46,6 +46,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("KLT_NVCC_EXTRA", "").split()   # e.g. -DKLT_LK_TIMELINE for scripts/lk_timeline.py / lk_phases.py
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -16,6 +16,8 @@
 //    the same test per class; (2) otherwise a serial float32 replay in OpenCV's order.
 #include "klt_common.cuh"
 
+#include <cstdlib>
+
 namespace klt {
 
 namespace {
@@ -43,7 +45,8 @@ struct Chains {
     static constexpr int G_WORDS = G_RES + 16;
     // b scratch: 8 SIMD chains (2 sums x 4 lanes) of int pairs (x, x+4) in visiting order, then 2 tail chains of floats
     static constexpr int NS = NV / 8;                                // 8-pixel SIMD steps per window row
-    static constexpr int SLEN = 2 * WH * NS;                         // ints per SIMD chain
+    static constexpr int SUSED = 2 * WH * NS;                        // ints per SIMD chain
+    static constexpr int SLEN = (SUSED + 3) / 4 * 4;                 // chain stride (zero padded: 0 + 0 -> +0.0f is a no-op)
     static constexpr int TLEN = (WH * TL + 3) / 4 * 4;               // floats per tail chain (zero padded)
     static constexpr int B_RES = 8 * SLEN + 2 * TLEN;                // 12 result words: q[0..3] of b1, of b2, t of b1, of b2
     static constexpr int B_WORDS = (B_RES + 12 + 3) / 4 * 4;
@@ -78,7 +81,9 @@ struct Cfg {
     static constexpr int NS = NV / 8;                         // 8-pixel SIMD steps per window row
     static constexpr int OFF_R3 = OFF_I + I_BYTES;            // [2][WPP] int4
     static constexpr int OFF_R16 = OFF_R3 + 2 * WPP * 16;     // [2][16 values][4 warps] int
-    static constexpr int POINT_BYTES = (OFF_R16 + 2 * 256 + 127) / 128 * 128;
+    static constexpr int OFF_GID = OFF_R16 + 2 * 256;         // the point's index (long long), parked here by thread 0 so
+                                                              // that it does not occupy two registers for the whole point
+    static constexpr int POINT_BYTES = (OFF_GID + 16 + 127) / 128 * 128;
 };
 
 __device__ __forceinline__ int dp2a_lo(uint32_t w, uint32_t b, int c)
@@ -92,6 +97,12 @@ __device__ __forceinline__ int dp2a_hi(uint32_t w, uint32_t b, int c)
     int d;
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c));
     return d;
+}
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
@@ -284,6 +295,65 @@ __device__ __forceinline__ void zero_pad_b(int* buf, int tid)
     using CH = Chains<WW, WH>;
     constexpr int PAD = CH::TLEN - WH * CH::TL;
     if (tid < 2 * PAD) buf[8 * CH::SLEN + (tid / (PAD > 0 ? PAD : 1)) * CH::TLEN + WH * CH::TL + tid % (PAD > 0 ? PAD : 1)] = 0;
+    constexpr int SPAD = CH::SLEN - CH::SUSED;
+    static_assert(8 * SPAD <= 32 && 2 * PAD <= 32, "one thread per padding word");
+    if (tid < 8 * SPAD) buf[(tid / (SPAD > 0 ? SPAD : 1)) * CH::SLEN + CH::SUSED + tid % (SPAD > 0 ? SPAD : 1)] = 0;
+}
+
+// The same replay for the resume teams, which have the registers to keep the loads ahead of the adds: the chain is then
+// bound by the dependent float adds alone (4 cycles each) instead of a shared-memory round trip per group of four.
+template <int N4>
+__device__ __forceinline__ float chain_sum_f4(const float4* __restrict__ src)
+{
+    constexpr int G = 8;
+    float4 cur[G], nxt[G];
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i) cur[i] = (i < N4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < N4; c += G) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) nxt[i] = (c + G + i < N4) ? src[c + G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (c + i < N4) acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, cur[i].x), cur[i].y), cur[i].z), cur[i].w);
+#pragma unroll
+        for (int i = 0; i < G; ++i) cur[i] = nxt[i];
+    }
+    return acc;
+}
+template <int N4>
+__device__ __forceinline__ float chain_sum_i4(const int4* __restrict__ src)
+{
+    constexpr int G = 8;
+    int4 cur[G], nxt[G];
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i) cur[i] = (i < N4) ? src[i] : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int c = 0; c < N4; c += G) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) nxt[i] = (c + G + i < N4) ? src[c + G + i] : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (c + i < N4) acc = __fadd_rn(__fadd_rn(acc, (float)(cur[i].x + cur[i].y)), (float)(cur[i].z + cur[i].w));
+#pragma unroll
+        for (int i = 0; i < G; ++i) cur[i] = nxt[i];
+    }
+    return acc;
+}
+template <int WW, int WH>
+__device__ __forceinline__ void replay_b_long(int* __restrict__ buf, int wip, int lane)
+{
+    using CH = Chains<WW, WH>;
+    if (wip == 0) {
+        const float acc = chain_sum_i4<CH::SLEN / 4>(reinterpret_cast<const int4*>(buf + (lane & 7) * CH::SLEN));
+        if (lane < 8) reinterpret_cast<float*>(buf)[CH::B_RES + lane] = acc;
+    }
+    if (wip == 1) {
+        const float acc = chain_sum_f4<CH::TLEN / 4>(reinterpret_cast<const float4*>(buf + 8 * CH::SLEN + (lane & 1) * CH::TLEN));
+        if (lane < 2) reinterpret_cast<float*>(buf)[CH::B_RES + 8 + lane] = acc;
+    }
 }
 
 // b replay, split over the point's warps: warp 0 runs the 8 SIMD chains (lane = chain; int pair -> float -> add), warp
@@ -315,29 +385,26 @@ __device__ __forceinline__ void replay_b(int* __restrict__ buf, int wip, int lan
     }
 }
 
-template <int WW, int WH, int WPP>
-__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
-lk_fast_kernel(const __grid_constant__ LKLaunch L)
+// Tracks one point through all levels (resume == nullptr) or resumes a handed-off point at (level, iteration j) of
+// *resume.  Returns false when the point exceeded the per-level iteration budget and was pushed onto the work list
+// (its outputs are then written by the team that resumes it).
+template <int WW, int WH, int WPP, bool LONG>
+__device__ __forceinline__ bool run_point(const LKLaunch& L, const long long gid0, const LKResume* __restrict__ resume,
+                                          uint8_t* ws, const int tid, const int bar)
 {
     using C = Cfg<WW, WH, WPP>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int lane = threadIdx.x & 31;
-    const int pic = threadIdx.x / C::NT;        // point within the CTA
-    const int tid = threadIdx.x - pic * C::NT;  // thread within the point
+    const int lane = tid & 31;
     const int wip = tid >> 5;                   // warp within the point
-    const int bar = 1 + pic;
-    const long long gid = (long long)blockIdx.x * C::PPC + pic;
-    const long long total = (long long)L.n_per_pair * L.batch;
-    if (gid >= total) return;  // uniform over the point's warps: its named barrier is never used
+    const long long gid = gid0;
     const int bidx = (int)(gid / L.n_per_pair);
 
-    uint8_t* ws = smem + pic * C::POINT_BYTES;
     uint8_t* jreg = ws + C::OFF_J;
     uint32_t* dreg = reinterpret_cast<uint32_t*>(ws + C::OFF_D);
     uint8_t* ireg = ws + C::OFF_I;
     int4* red3 = reinterpret_cast<int4*>(ws + C::OFF_R3);
     int* red16 = reinterpret_cast<int*>(ws + C::OFF_R16);
     int par3 = 0, par16 = 0;
+    if (tid == 0) *reinterpret_cast<volatile long long*>(ws + C::OFF_GID) = gid;   // read back by the same thread only
 
     // units of this thread: unit u = tid + k*NT covers window pixels (y, x0..x0+3); coordinates are recomputed where
     // needed (division by a constant), only the word offset inside the staged next-image region is kept.
@@ -347,19 +414,42 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
     int jw[C::UPT];
 #pragma unroll
     for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
+    // resume teams: where a unit's mismatch products go in the replay scratch (word offsets), tail unit?, last unit of a row?
+    int coff[LONG ? C::UPT : 1];
+    bool ctail[LONG ? C::UPT : 1];
+    int cnv[LONG ? C::UPT : 1];
+    if constexpr (LONG) {
+        using CH = Chains<WW, WH>;
+#pragma unroll
+        for (int k = 0; k < C::UPT; ++k) {
+            const int y = unit_y(k), x0 = unit_x0(k);
+            ctail[k] = x0 >= C::NV;
+            cnv[k] = min(4, WW - x0);
+            coff[k] = ctail[k] ? 8 * CH::SLEN + y * CH::TL + (x0 - C::NV) : (y * CH::NS + (x0 >> 3)) * 2 + ((x0 >> 2) & 1);
+        }
+    }
 
     const long long t_start = clock64();
+#ifdef KLT_LK_TIMELINE
+    const unsigned long long t_g0 = (L.flags & 0x400) ? gtimer() : 0ull;   // debug flag 0x400: start / end stamps (128 ns units)
+    long long ph[6] = {0, 0, 0, 0, 0, 0};   // debug flag 0x200: cycles per phase of the long-point iteration
+#endif
     int n_t1 = 0, n_t2 = 0;
     const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
     float2 outp = make_float2(0.f, 0.f);
     if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) outp = reinterpret_cast<const float2*>(L.next_pts)[gid];
     int status = 1;
     float err = 0.f;
-    int iters = 0;
+    bool handed = false;
+    int iters = resume ? resume->iters : 0;
     const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
     const int top = L.prev.top;
+    const int first = resume ? resume->level : top;   // a resumed point re-enters at the level it left
+    // iterations a point may spend on one level before it is handed to a resume team (0 = no hand-off)
+    // (the host leaves L.budget = 0 when no work list is attached)
 
-    for (int level = top; level >= 0; --level) {
+    for (int level = first; level >= 0; --level) {
+        const bool resuming = resume != nullptr && level == first;
         const LevelView lvI = L.prev.lv[level];
         const LevelView lvJ = L.next.lv[level];
         const uint8_t* __restrict__ imgI = lvI.data + (long long)bidx * lvI.batch_stride;
@@ -369,7 +459,10 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
 
         float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
         float nx, ny;
-        if (level == top) {
+        if (resuming) {
+            // position at the start of iteration resume->j, i.e. what the update of iteration j - 1 stored (j >= 1)
+            nx = __fadd_rn(resume->nx, hwx); ny = __fadd_rn(resume->ny, hwy);
+        } else if (level == top) {
             if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(outp.x, scale); ny = __fmul_rn(outp.y, scale); }
             else { nx = px; ny = py; }
         } else {
@@ -387,6 +480,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
         nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+        if (resuming) { nx = resume->nx; ny = resume->ny; }
         // ---- stage both neighbourhoods; the previous level's readers are done (barrier below) -------------
         point_sync<WPP>(bar);
         int jax = 0, jy0 = 0, jx0 = 0;  // region origin: smem col 0 <-> image x = jax; window columns start at jx0
@@ -624,20 +718,95 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             }
         };
 
-        float pdx = 0.f, pdy = 0.f;
-        bool sticky = false, pads_zeroed = false;
-        for (int j = 0; j < L.max_count; ++j) {
+        float pdx = resuming ? resume->pdx : 0.f, pdy = resuming ? resume->pdy : 0.f;
+        bool sticky = resuming, pads_zeroed = false;
+        for (int j = resuming ? resume->j : 0; j < L.max_count; ++j) {
+            if (!LONG && j == L.budget && L.budget > 0) {
+                // Long point (99.4 % of the (point, level) pairs of a KITTI frame converge within 6 iterations): it would
+                // bound the launch while occupying a slot of the bulk shape, so it continues on a resume team.
+                if (tid == 0) {
+                    const int slot = atomicAdd(L.wl_ctrl, 1);
+                    push_entry(L, slot, *reinterpret_cast<volatile long long*>(ws + C::OFF_GID), level, j, nx, ny, pdx, pdy, iters);
+                }
+                handed = true;
+                break;
+            }
             int inx, iny;
             if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
                 if (level == 0) status = 0;
                 break;
             }
             ++iters;
+#ifdef KLT_LK_TIMELINE
+            long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;
+            if constexpr (LONG) tq0 = clock64();
+#define KLT_TQ(v) v = clock64()
+#else
+#define KLT_TQ(v)
+#endif
             ensure_j(inx, iny);
             int v00, v01, v10, v11;
             q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
             const uint32_t W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
             const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
+            float b1 = 0.f, b2 = 0.f;
+            if constexpr (LONG) {
+                // Resume teams: the points they serve failed the exactness bounds on nearly every iteration of the bulk
+                // shape, so the mismatch products go straight into OpenCV's accumulation chains (always exact).
+                using CH = Chains<WW, WH>;
+                int* buf = reinterpret_cast<int*>(dreg);
+                if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }
+                const int cb = (iny - jy0) * C::SJ + (inx - jax);
+                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
+                const int sh = (cb & 3) * 8;
+                ++n_t2;
+                KLT_TQ(tq1);
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const uint32_t* __restrict__ r0 = jbase + jw[k];
+                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
+                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
+                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
+                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1_ = __funnelshift_rc(q0, q1, sh + 8);
+                    int jv[4];
+                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                    jv[1] = dp2a_lo(W1, b1_, dp2a_lo(W0, b0, 256)) >> 9;
+                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                    jv[3] = dp2a_hi(W1, b1_, dp2a_hi(W0, b0, 256)) >> 9;
+                    if (unit_ok(k)) {
+                        if (ctail[k]) {
+                            float* tf = reinterpret_cast<float*>(buf) + coff[k];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (jj < cnv[k]) {
+                                    const int d = jv[jj] - pxs[k][jj].iv();
+                                    tf[jj] = (float)(d * pxs[k][jj].gx());
+                                    tf[CH::TLEN + jj] = (float)(d * pxs[k][jj].gy());
+                                }
+                        } else {
+                            int* si = buf + coff[k];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int d = jv[jj] - pxs[k][jj].iv();
+                                si[jj * CH::SLEN] = d * pxs[k][jj].gx();
+                                si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
+                            }
+                        }
+                    }
+                }
+                KLT_TQ(tq2);
+                point_sync<WPP>(bar);
+                KLT_TQ(tq3);
+                replay_b_long<WW, WH>(buf, wip, lane);
+                KLT_TQ(tq4);
+                point_sync<WPP>(bar);
+                KLT_TQ(tq5);
+                const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
+                const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
+                const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
+                b1 = combine5(r1.x, r1.y, r1.z, r1.w, rt.x);
+                b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
+            } else {
             DiffStore<C::PACK> dd[C::UPT];
             int s1, s2, bnd;
             {
@@ -670,7 +839,6 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             }
             // Tier 0 (whole-window bound) unless the previous iteration of this point already failed it ("sticky"):
             // diverging points fail it every time, and they are the ones that bound the launch latency.
-            float b1 = 0.f, b2 = 0.f;
             bool classes = sticky;
             if (!sticky) {
                 // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamp so the point total cannot wrap
@@ -766,6 +934,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
                 }
             }
+            }   // !LONG
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -784,7 +953,17 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 break;
             }
             pdx = dx; pdy = dy;
+#ifdef KLT_LK_TIMELINE
+            if constexpr (LONG) {
+                if (L.flags & 0x200) {
+                    const long long tq6 = clock64();
+                    ph[0] += tq1 - tq0; ph[1] += tq2 - tq1; ph[2] += tq3 - tq2; ph[3] += tq4 - tq3; ph[4] += tq5 - tq4; ph[5] += tq6 - tq5;
+                }
+            }
+#endif
         }
+
+        if (handed) break;   // (no early return: the warp collectives above must stay provably convergent)
 
         // ---- err at level 0 ------------------------------------------------------------------------------------
         if (status && level == 0 && (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) == 0) {
@@ -828,13 +1007,152 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         }
     }
 
-    if (tid == 0) {
+    if (tid == 0 && !handed) {
+        const long long gid = *reinterpret_cast<volatile long long*>(ws + C::OFF_GID);
         reinterpret_cast<float2*>(L.next_pts)[gid] = outp;
         L.status[gid] = (uint8_t)status;
         L.err[gid] = err;
         if (L.iters) {
             // debug flag 0x100: cycles / 64 in the low 20 bits, tier-1 and tier-2 counts above (profiling aid)
+#ifdef KLT_LK_TIMELINE
+            if (L.flags & 0x400) L.iters[gid] = (int)((t_g0 >> 7) & 0x7fff) | (int)(((gtimer() >> 7) & 0x7fff) << 15) | ((LONG ? 1 : 0) << 30);
+            else if (LONG && (L.flags & 0x200)) L.iters[gid] = (int)(ph[(L.flags >> 12) & 7] >> 2) | (wip << 28);
+            else
+#endif
             L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
+        }
+    }
+    return !handed;
+}
+
+// Bulk shape: one team of WPP warps per point.  With a work list attached (L.wl), a point that spends L.budget iterations
+// on one level stops there and is pushed onto the list; lk_long_kernel, running beside this kernel, finishes it.
+//
+// Two-phase grid (L.two_phase, the latency shape): the points that bound the launch are almost always border points
+// (their match leaves the frame), and a point found to be long in the last wave would finish a whole long-point latency
+// after the rest.  So the first n_bulk_blocks CTAs only keep the border suspects (everything else is appended to the
+// "normal" list and the CTA exits within a microsecond), and a second range of n_bulk_blocks CTAs serves that list: the
+// hardware dispatches CTAs in index order, so every suspect starts in the first microseconds of the launch and the long
+// ones among them reach the long-point kernel early.  Nothing in phase 1 waits, so the order is a performance
+// assumption only.
+template <int WW, int WH, int WPP>
+__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
+lk_fast_kernel(const __grid_constant__ LKLaunch L)
+{
+    using C = Cfg<WW, WH, WPP>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int pic = threadIdx.x / C::NT;        // point within the CTA
+    const int tid = threadIdx.x - pic * C::NT;  // thread within the point
+    const long long gid = (long long)blockIdx.x * C::PPC + pic;
+    if (gid >= (long long)L.n_per_pair * L.batch) return;  // uniform over the point's warps: its named barrier is never used
+    run_point<WW, WH, WPP, false>(L, gid, nullptr, smem + pic * C::POINT_BYTES, tid, 1 + pic);
+    if (L.wl != nullptr && tid == 0) {
+        __threadfence();            // the work-list entry (if any) is visible before the sign-off
+        atomicAdd(L.wl_ctrl + kCtrlFinished, 1);
+    }
+}
+
+// The two-phase form of the same kernel (see above); a kernel of its own because the divergent waiting code in front of
+// the point makes the compiler wrap every warp collective of the point in convergence barriers.
+template <int WW, int WH, int WPP>
+__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
+lk_fast2p_kernel(const __grid_constant__ LKLaunch L)
+{
+    using C = Cfg<WW, WH, WPP>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int pic = threadIdx.x / C::NT;
+    const int tid = threadIdx.x - pic * C::NT;
+    const int bar = 1 + pic;
+    uint8_t* ws = smem + pic * C::POINT_BYTES;
+    const long long total = (long long)L.n_per_pair * L.batch;
+    long long gid;
+    if ((long long)blockIdx.x < L.n_bulk_blocks) {
+        gid = (long long)blockIdx.x * C::PPC + pic;
+        if (gid >= total) return;
+        const float2 p = reinterpret_cast<const float2*>(L.prev_pts)[gid];
+        const float m = L.suspect_margin;
+        const float w0 = (float)L.prev.lv[0].w - 1.f - m, h0 = (float)L.prev.lv[0].h - 1.f - m;
+        // (votes make the branch conditions warp-uniform for the compiler: otherwise every warp collective of the point is
+        // wrapped in convergence barriers -- 2x the REDUX count and WARPSYNC around each)
+        const bool suspect = __any_sync(kFull, p.x < m || p.y < m || p.x > w0 || p.y > h0);
+        if (tid == 0) {
+            if (!suspect) L.nl[atomicAdd(L.wl_ctrl + kCtrlNormal, 1)] = (int)gid;
+            __threadfence();
+            atomicAdd(L.wl_ctrl + kCtrlDecided, 1);
+        }
+        if (!suspect) return;
+    } else {
+        const long long e = ((long long)blockIdx.x - L.n_bulk_blocks) * C::PPC + pic;
+        if (e >= total) return;
+        volatile int* ctrl = L.wl_ctrl;
+        int spins = 0;
+        while (__any_sync(kFull, ctrl[kCtrlDecided] < total) && ++spins < (1 << 24)) __nanosleep(100);   // every thread polls: uniform control flow
+        __threadfence();
+        const int n_normal = ctrl[kCtrlNormal];   // final once every phase-1 CTA has decided
+        if (__any_sync(kFull, e >= n_normal)) return;
+        gid = __ldcg(L.nl + e);
+    }
+    run_point<WW, WH, WPP, false>(L, gid, nullptr, ws, tid, bar);
+    if (tid == 0) {
+        __threadfence();            // the work-list entry (if any) is visible before the sign-off
+        atomicAdd(L.wl_ctrl + kCtrlFinished, 1);
+    }
+}
+
+// Long points: one CTA of 4 warps per work-list entry (entries e, e + gridDim.x, ...), tuned for the latency of one
+// iteration instead of throughput (launch bounds leave the registers for the pipelined replay).  The kernel may run
+// beside the bulk kernel (side stream): a CTA waits until its entry exists or every bulk point has signed off -- the
+// bulk path never waits for this kernel, so there is no cyclic dependency; a bounded spin turns a missing bulk launch
+// into an early exit instead of a hang.  The last CTA to leave zeroes the control words for the next launch.
+template <int WW, int WH>
+__global__ void __launch_bounds__(kThreads, 4)   // 128 registers: one CTA of this kernel + 4 of the bulk kernel fill an SM's register file
+lk_long_kernel(const __grid_constant__ LKLaunch L)
+{
+    using C = Cfg<WW, WH, 4>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int have_s;
+    const int tid = threadIdx.x;
+    const long long total = (long long)L.n_per_pair * L.batch;
+    volatile int* ctrl = L.wl_ctrl;
+    for (long long e = blockIdx.x;; e += gridDim.x) {
+        if (tid == 0) {
+            int have = 0;
+            for (long long spins = 0; spins < (1LL << 24); ++spins) {
+                const long long done = ctrl[kCtrlFinished];
+                __threadfence();
+                const long long cnt = ctrl[kCtrlPushed];   // read after `done`: final once done == total
+                if (cnt > e) { have = 1; break; }
+                if (done >= total) break;
+                __nanosleep(100);
+            }
+            __threadfence();
+            have_s = have;
+        }
+        __syncthreads();
+        const int have = have_s;
+        __syncthreads();
+        if (!have) break;
+        LKResume r;
+        {
+            const int4* src = reinterpret_cast<const int4*>(L.wl + e);
+            const volatile int* ep = reinterpret_cast<const volatile int*>(src + 2) + 3;
+            for (int spins = 0; *ep != L.epoch && spins < (1 << 22); ++spins) {}   // the producer is between counter and payload
+            __threadfence();
+            const int4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);
+            r.gid = ((long long)(unsigned)a.x) | ((long long)a.y << 32);
+            r.level = a.z; r.j = a.w;
+            r.nx = __int_as_float(b.x); r.ny = __int_as_float(b.y); r.pdx = __int_as_float(b.z); r.pdy = __int_as_float(b.w);
+            r.iters = c.x; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        }
+        run_point<WW, WH, 4, true>(L, r.gid, &r, smem, tid, 1);
+        __syncthreads();   // the next entry reuses the scratch
+    }
+    if (tid == 0) {
+        const int gone = atomicAdd(L.wl_ctrl + kCtrlLongGone, 1);
+        if (gone == (int)gridDim.x - 1) {
+            L.wl_ctrl[kCtrlPushed] = 0; L.wl_ctrl[kCtrlNormal] = 0; L.wl_ctrl[kCtrlDecided] = 0; L.wl_ctrl[kCtrlFinished] = 0;
+            __threadfence();
+            L.wl_ctrl[kCtrlLongGone] = 0;
         }
     }
 }
@@ -849,24 +1167,84 @@ klt_status launch_fast(const LKLaunch& L, cudaStream_t stream)
     const size_t smem = (size_t)C::POINT_BYTES * C::PPC;
     if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(lk_fast_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lk_fast2p_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (klt_status)e;
     }
+    if (L.n_per_pair < 0) return KLT_OK;   // configure only (loads the kernel before anything is launched)
     const long long total = (long long)L.n_per_pair * L.batch;
     const long long blocks = (total + C::PPC - 1) / C::PPC;
-    if (blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    lk_fast_kernel<WW, WH, WPP><<<(unsigned)blocks, kThreads, smem, stream>>>(L);
-    cudaError_t e = cudaGetLastError();
+    if (blocks > 0x3fffffffLL) return KLT_ERR_UNSUPPORTED;
+    LKLaunch K = L;
+    K.n_bulk_blocks = blocks;
+    if (K.two_phase) lk_fast2p_kernel<WW, WH, WPP><<<(unsigned)(2 * blocks), kThreads, smem, stream>>>(K);
+    else lk_fast_kernel<WW, WH, WPP><<<(unsigned)blocks, kThreads, smem, stream>>>(K);
+    const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
 template <int WW, int WH>
-klt_status launch_wpp(const LKLaunch& L, int wpp, cudaStream_t stream)
+klt_status launch_long(const LKLaunch& L, cudaStream_t stream)
 {
-    switch (wpp) {
-        case 1: return launch_fast<WW, WH, 1>(L, stream);
-        case 2: return launch_fast<WW, WH, 2>(L, stream);
-        default: return launch_fast<WW, WH, 4>(L, stream);
+    using CL = Cfg<WW, WH, 4>;
+    static PerDeviceOnce configured;
+    if (configured.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(lk_long_kernel<WW, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL::POINT_BYTES);
+        if (e != cudaSuccess) return (klt_status)e;
     }
+    if (L.n_per_pair < 0) return KLT_OK;   // configure only
+    lk_long_kernel<WW, WH><<<(unsigned)L.n_resume_blocks, kThreads, (size_t)CL::POINT_BYTES, stream>>>(L);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
+}
+
+template <int WW, int WH>
+klt_status launch_window(const LKLaunch& L, int wpp, bool team_bulk, cudaStream_t stream)
+{
+    LKLaunch K = L;
+    // the team shape hands off on the budget only; the warp shape also when a float32 sum really rounds
+    if (K.budget >= K.max_count) K.budget = 0;
+    const bool handoff = K.wl != nullptr && K.n_resume_blocks > 0 && (K.budget > 0 || !team_bulk);
+    if (!handoff) { K.wl = nullptr; K.wl_ctrl = nullptr; K.nl = nullptr; K.budget = 0; K.n_resume_blocks = 0; }
+    const bool concurrent = handoff && team_bulk && K.budget > 0 && K.two_phase && K.nl && K.side_stream && K.ev_fork && K.ev_join;
+    K.two_phase = concurrent ? 1 : 0;
+    auto launch_bulk = [&](const LKLaunch& B) {
+        if (!team_bulk) return lk_launch_warp(B, stream);
+        if (wpp == 1) return launch_fast<WW, WH, 1>(B, stream);
+        if (wpp == 2) return launch_fast<WW, WH, 2>(B, stream);
+        return launch_fast<WW, WH, 4>(B, stream);
+    };
+    if (concurrent) {
+        // Both kernels are configured (and thereby loaded) before either is launched: loading a kernel can synchronise
+        // the device, and the long-point kernel would sit in its bounded spin meanwhile.  The bulk kernel is launched
+        // first; the long-point kernel follows on the high-priority side stream, so its CTAs (one per SM) take the first
+        // slots the bulk frees -- within a microsecond, because the non-suspect CTAs of phase 1 leave at once.
+        LKLaunch cfg = K;
+        cfg.n_per_pair = -1;
+        klt_status s = launch_bulk(cfg);
+        if (s == KLT_OK) s = launch_long<WW, WH>(cfg, stream);
+        if (s != KLT_OK) return s;
+        cudaStream_t side = static_cast<cudaStream_t>(K.side_stream);
+        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(K.ev_fork), stream);
+        if (e != cudaSuccess) return (klt_status)e;
+        s = launch_bulk(K);
+        if (s != KLT_OK) return s;
+        // from here on a failure leaves the bulk's long points unfinished (the caller sees the error) and the control
+        // words dirty: they are cleared behind the bulk kernel so that the next launch starts clean
+        e = cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(K.ev_fork), 0);
+        if (e == cudaSuccess) {
+            s = launch_long<WW, WH>(K, side);
+            if (s == KLT_OK) {
+                e = cudaEventRecord(static_cast<cudaEvent_t>(K.ev_join), side);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(K.ev_join), 0);
+                if (e == cudaSuccess) return KLT_OK;
+            }
+        }
+        cudaMemsetAsync(K.wl_ctrl, 0, 64, stream);
+        return s != KLT_OK ? s : (klt_status)e;
+    }
+    klt_status s = launch_bulk(K);
+    if (s != KLT_OK || !handoff) return s;
+    return launch_long<WW, WH>(K, stream);
 }
 
 }  // namespace
@@ -875,14 +1253,16 @@ klt_status launch_wpp(const LKLaunch& L, int wpp, cudaStream_t stream)
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream)
 {
     const long long total = (long long)L.n_per_pair * L.batch;
-    // warps per point, from measurements on B200 (profiles/): the kernel is latency-bound, so more warps per point win
-    // until the per-iteration overhead replicated in every warp dominates: 31x31 -> always 4; 21x21 -> 4 while the
-    // points fit the chip about once, else 2.  One warp per point never wins (register-limited occupancy).
+    // Bulk shape: teams of WPP warps per point, patch in registers: 31x31 -> 4 warps; 21x21 -> 4 while the points fit
+    // the chip about once, else 2 (KLT_LK_WPP forces it).  KLT_LK_SHAPE=warp selects the one-warp-per-point shape of
+    // klt_lk_warp.cu for A/B runs (measured slower on B200).
+    static const char* shape = getenv("KLT_LK_SHAPE");
+    const bool team_bulk = !(shape && shape[0] == 'w');
     int wpp = 4;
     if (L.win_w * L.win_h <= 21 * 21 && total > (long long)sm_count * 32) wpp = 2;
     if (forced_wpp == 1 || forced_wpp == 2 || forced_wpp == 4) wpp = forced_wpp;
-    if (L.win_w == 21 && L.win_h == 21) return launch_wpp<21, 21>(L, wpp, stream);
-    if (L.win_w == 31 && L.win_h == 31) return launch_wpp<31, 31>(L, wpp, stream);
+    if (L.win_w == 21 && L.win_h == 21) return launch_window<21, 21>(L, wpp, team_bulk, stream);
+    if (L.win_w == 31 && L.win_h == 31) return launch_window<31, 31>(L, wpp, team_bulk, stream);
     return KLT_ERR_UNSUPPORTED;
 }
 

@@ -129,7 +129,7 @@ def lk_track(prev, nxt, prevPts, nextPts=None, criteria=(3, 30, 0.01), flags=0, 
         out = torch.empty_like(pts)
     status = torch.empty((B, N), dtype=torch.uint8, device=dev)
     err = torch.empty((B, N), dtype=torch.float32, device=dev)
-    iters = torch.empty((B, N), dtype=torch.int32, device=dev) if return_iters else None
+    iters = torch.zeros((B, N), dtype=torch.int32, device=dev) if return_iters else None
     if N > 0:
         params = make_params(prev.win, criteria, flags, minEigThreshold)
         L = _lib.load()
