@@ -36,6 +36,9 @@ struct klt_ctx {
     struct LKScratch { cudaStream_t stream; int* ctrl; int* nl; LKResume* wl; long long capacity; cudaStream_t side; cudaEvent_t ev_fork, ev_join; int epoch; };
     std::vector<LKScratch> lk_scratch;
     std::mutex lk_mutex;
+    // completion counters of the one-launch pyramid build, one array per stream and geometry (klt_pyramid.cu)
+    struct PyrScratch { cudaStream_t stream; unsigned* cnt; long long capacity; unsigned gen; long long key[6]; };
+    std::vector<PyrScratch> pyr_scratch;
 };
 
 namespace {
@@ -145,6 +148,62 @@ klt_status attach_lk_scratch(klt_ctx* ctx, cudaStream_t stream, LKLaunch& L)
         if (!env_resume) L.n_resume_blocks = ctx->sm_count / 2;
     }
     return KLT_OK;
+}
+
+// All levels of the item range in ONE launch (pyr_build_fused_kernel); KLT_ERR_UNSUPPORTED: launch level by level.
+klt_status pyr_build_one_launch(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* lay, uint8_t* d_pyr, int first_item,
+                                int n_items, cudaStream_t stream)
+{
+    const int n_steps = lay->top;
+    const uint8_t* src[KLT_MAX_LEVELS];
+    uint8_t* dst[KLT_MAX_LEVELS];
+    int w[KLT_MAX_LEVELS], h[KLT_MAX_LEVELS];
+    long long sp[KLT_MAX_LEVELS], sb[KLT_MAX_LEVELS], dp[KLT_MAX_LEVELS], db[KLT_MAX_LEVELS];
+    for (int l = 0; l < n_steps; ++l) {
+        const klt_level& a = lay->level[l];
+        const klt_level& b = lay->level[l + 1];
+        src[l] = ((l == 0) ? d_img : d_pyr + a.offset) + (int64_t)first_item * a.batch_stride;
+        dst[l] = d_pyr + b.offset + (int64_t)first_item * b.batch_stride;
+        w[l] = a.w; h[l] = a.h; sp[l] = a.pitch; sb[l] = a.batch_stride; dp[l] = b.pitch; db[l] = b.batch_stride;
+    }
+    PyrFused P;
+    long long n_cnt = 0;
+    klt_status s = pyr_fused_plan(P, n_steps, src, dst, w, h, sp, sb, dp, db, n_items, ctx->sm_count, &n_cnt);
+    if (s != KLT_OK) return s;
+    // the counter layout depends on the geometry only (not on which items are built): one array per stream and geometry
+    const long long key[6] = {lay->level[0].w, lay->level[0].h, n_steps, n_items, lay->level[0].pitch, P.s[0].rows};
+    std::lock_guard<std::mutex> guard(ctx->lk_mutex);
+    klt_ctx::PyrScratch* slot = nullptr;
+    for (auto& sc : ctx->pyr_scratch)
+        if (sc.stream == stream && std::memcmp(sc.key, key, sizeof(key)) == 0) { slot = &sc; break; }
+    if (!slot) {
+        if (ctx->pyr_scratch.size() >= 64) {          // many geometries on many streams: recycle (rare; costs a sync)
+            KLT_CUDA(cudaDeviceSynchronize());
+            for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
+            ctx->pyr_scratch.clear();
+        }
+        klt_ctx::PyrScratch fresh = {stream, nullptr, n_cnt, 0u, {key[0], key[1], key[2], key[3], key[4], key[5]}};
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (size_t)(n_cnt > 0 ? n_cnt : 1) * sizeof(unsigned));
+        if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+        e = cudaMemset(p, 0, (size_t)(n_cnt > 0 ? n_cnt : 1) * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the memset is not ordered with non-blocking streams
+        if (e != cudaSuccess) { cudaFree(p); return (klt_status)e; }
+        fresh.cnt = static_cast<unsigned*>(p);
+        try { ctx->pyr_scratch.push_back(fresh); } catch (const std::bad_alloc&) { cudaFree(p); return KLT_ERR_OUT_OF_MEMORY; }
+        slot = &ctx->pyr_scratch.back();
+    }
+    if (slot->gen >= 0x0fffffffu) {                   // counters would wrap: start over (once per 2.7e8 launches)
+        KLT_CUDA(cudaStreamSynchronize(stream));
+        KLT_CUDA(cudaMemset(slot->cnt, 0, (size_t)(slot->capacity > 0 ? slot->capacity : 1) * sizeof(unsigned)));
+        KLT_CUDA(cudaDeviceSynchronize());
+        slot->gen = 0;
+    }
+    P.cnt = slot->cnt;
+    P.gen = ++slot->gen;
+    s = pyr_fused_launch(P, stream);
+    if (s != KLT_OK) --slot->gen;
+    return s;
 }
 
 void make_view(const klt_pyr_layout* lay, const uint8_t* img, const uint8_t* pyr, int first_item, int item_stride, PyrView& v)
@@ -258,6 +317,7 @@ klt_status klt_destroy(klt_ctx* ctx)
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->h_ws) cudaFreeHost(ctx->h_ws);
     cudaDeviceSynchronize();   // caller streams that used the work lists may be gone already
+    for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
     for (auto& sc : ctx->lk_scratch) {
         if (sc.ctrl) cudaFree(sc.ctrl);
         if (sc.side) cudaStreamDestroy(sc.side);
@@ -339,10 +399,16 @@ klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layou
     if (layout->top > 0 && !d_pyr) return KLT_ERR_INVALID_ARG;
     if (n_items <= 0) { first_item = 0; n_items = layout->batch; }
     if (first_item < 0 || first_item + n_items > layout->batch) return KLT_ERR_INVALID_ARG;
+    for (int l = 0; l < layout->top; ++l)
+        if (layout->level[l + 1].w != (layout->level[l].w + 1) / 2 || layout->level[l + 1].h != (layout->level[l].h + 1) / 2) return KLT_ERR_INVALID_ARG;
+    static const char* env_fused = getenv("KLT_PYR_ONE_LAUNCH");   // A/B runs: 0 = one launch per level (round 1)
+    if (layout->top >= 2 && !(env_fused && env_fused[0] == '0')) {
+        s = pyr_build_one_launch(ctx, d_img, layout, d_pyr, first_item, n_items, (cudaStream_t)stream);
+        if (s != KLT_ERR_UNSUPPORTED) return s;
+    }
     for (int l = 0; l < layout->top; ++l) {
         const klt_level& a = layout->level[l];
         const klt_level& b = layout->level[l + 1];
-        if (b.w != (a.w + 1) / 2 || b.h != (a.h + 1) / 2) return KLT_ERR_INVALID_ARG;
         const uint8_t* src = ((l == 0) ? d_img : d_pyr + a.offset) + (int64_t)first_item * a.batch_stride;
         if (l >= 1 && l + 2 <= layout->top) {
             // levels >= 1 are small: two of them per launch (level 0 -> 1 stays with the HBM-bound streaming kernel)

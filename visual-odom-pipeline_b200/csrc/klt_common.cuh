@@ -58,6 +58,28 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
                            uint8_t* dst, long long dpitch, long long dbatch, int batch, int sm_count,
                            cudaStream_t stream);
 
+// Whole pyramid in one launch (klt_pyramid.cu: pyr_build_fused_kernel)
+struct PyrStep {
+    const uint8_t* src;
+    uint8_t* dst;
+    long long spitch, sbatch, dpitch, dbatch;
+    int w, h, dw, dh;
+    int rows, tiles_x, n8, rem_nout, strips_y;   // warp tasks of the step: tiles_x x strips_y x batch
+    int cnt_off;                                 // first completion counter of the step ([image][strip])
+    long long task_begin;
+};
+struct PyrFused {
+    PyrStep s[KLT_MAX_LEVELS - 1];
+    int n_steps, batch;
+    long long n_tasks;
+    unsigned* cnt;      // completion counters, monotonic: a strip of launch number `gen` is complete at gen * tiles_x
+    unsigned gen;
+};
+klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, uint8_t* const* dst, const int* w, const int* h,
+                          const long long* spitch, const long long* sbatch, const long long* dpitch, const long long* dbatch,
+                          int batch, int sm_count, long long* n_counters);
+klt_status pyr_fused_launch(const PyrFused& P, cudaStream_t stream);
+
 // Two pyramid levels (l -> l+1 -> l+2) in one launch; KLT_ERR_UNSUPPORTED for shapes it does not take.
 klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0, long long batch0,
                             uint8_t* mid, long long pitch1, long long batch1, uint8_t* dst, long long pitch2, long long batch2,

@@ -784,6 +784,78 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Whole pyramid in ONE launch.  The task list is [all tasks of level 0 -> 1 | all of 1 -> 2 | ...] over the same warp
+// tasks as pyr_down_ring_kernel; a task of step l >= 1 first waits until the strips of level l that hold its input rows
+// are complete: every producer task ends with fence + one atomicAdd on its (image, strip) counter, and a counter is
+// complete at gen * tiles_x (gen = launches so far on this counter array, so nothing is zeroed between launches).
+// Producers always have lower task indices than their consumers and CTAs are dispatched in index order, and a waiting
+// warp holds no resource a producer needs, so the wait cannot deadlock; it is bounded anyway.
+// Why: the small levels are launch- and tail-bound on their own (level 1 -> 2: 40 %, 2 -> 3: 18 % of the copy peak for
+// 310 KITTI frames, 3 x 4 us of launch latency for a single pair); in one grid they run in the shadow of level 0 -> 1.
+template <int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
+{
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (task >= P.n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+    int l = 0;
+    while (l + 1 < P.n_steps && task >= P.s[l + 1].task_begin) ++l;
+    const PyrStep& S = P.s[l];
+    const long long local = task - S.task_begin;
+    const int tx = (int)(local % S.tiles_x);
+    const long long t2 = local / S.tiles_x;
+    const int sy = (int)(t2 % S.strips_y);
+    const int b = (int)(t2 / S.strips_y);
+    const int y0 = sy * S.rows;
+    const int y1 = min(y0 + S.rows, S.dh);
+    if (l > 0) {
+        const PyrStep& Q = P.s[l - 1];              // produced this step's source level
+        const int s_lo = max(2 * y0 - 2, 0) / Q.rows;
+        const int s_hi = min(min(2 * y1, S.h - 1) / Q.rows, Q.strips_y - 1);
+        const unsigned target = P.gen * (unsigned)Q.tiles_x;
+        const volatile unsigned* c = P.cnt + Q.cnt_off + (long long)b * Q.strips_y;
+        for (int k = s_lo + lane; k <= s_hi; k += 32) {
+            int spins = 0;
+            while ((int)(c[k] - target) < 0 && ++spins < (1 << 24)) __nanosleep(64);
+        }
+        __threadfence();
+        __syncwarp();
+    }
+    const uint8_t* __restrict__ simg = S.src + (long long)b * S.sbatch;
+    uint8_t* __restrict__ dimg = S.dst + (long long)b * S.dbatch;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * RingCfg<8>::WARP_BYTES);
+    const int X0 = tx * RingCfg<8>::BODY;
+    if (tx < S.n8 || S.rem_nout == 8) ring_task<8>(simg, S.w, S.h, S.spitch, dimg, S.dw, S.dpitch, X0, y0, y1, ring_s, lane);
+    else ring_task<4>(simg, S.w, S.h, S.spitch, dimg, S.dw, S.dpitch, X0, y0, y1, ring_s, lane);
+    if (l + 1 < P.n_steps) {
+        __threadfence();                             // this lane's output bytes before the counter
+        __syncwarp();
+        if (lane == 0) atomicAdd(P.cnt + S.cnt_off + (long long)b * S.strips_y + sy, 1u);
+    }
+}
+
+// strip height of one step: see launch_ring
+static int ring_rows(int dh, int tiles_x, int batch, long long resident)
+{
+    static const char* force_rows = getenv("KLT_PYR_ROWS");   // tuning aid
+    if (force_rows && atoi(force_rows) >= 2) return min(atoi(force_rows), dh);
+    int rows = 2;
+    double best = 1e300;
+    for (int r = 2; r <= 48; ++r) {
+        const int strips = (dh + r - 1) / r;
+        const int rr = (dh + strips - 1) / strips;   // balanced strips of that count
+        const long long tasks = (long long)tiles_x * strips * batch;
+        const long long rounds = (tasks + resident - 1) / resident;
+        const double cost = (double)rounds * (2.0 * rr + 3.0 + 6.0);
+        if (cost < best) { best = cost; rows = rr; }
+    }
+    return rows;
+}
+
 template <int NOUT, bool ALIGNED>
 klt_status launch_t(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst,
                     int dw, int dh, long long dpitch, long long dbatch, int batch, int sm_count,
@@ -964,6 +1036,58 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
                     : launch_t<4, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
     }
     return launch_t<4, false>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+}
+
+// Plans the one-launch pyramid build (n_steps pyrDown steps; step i: src[i] -> dst[i], dst[i] == src[i + 1]).  Returns the
+// number of counters the launch needs in *n_counters (layout valid for this geometry only), KLT_ERR_UNSUPPORTED when a
+// level cannot take the ring kernel (unaligned rows, tiny images) -- the caller then launches level by level.
+klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, uint8_t* const* dst, const int* w, const int* h,
+                          const long long* spitch, const long long* sbatch, const long long* dpitch, const long long* dbatch,
+                          int batch, int sm_count, long long* n_counters)
+{
+    if (n_steps < 1 || n_steps > KLT_MAX_LEVELS - 1 || batch <= 0) return KLT_ERR_UNSUPPORTED;
+    using RC = RingCfg<8>;
+    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
+    long long tasks = 0, counters = 0;
+    for (int i = 0; i < n_steps; ++i) {
+        PyrStep& S = P.s[i];
+        const bool aligned = (((uintptr_t)src[i] | (uintptr_t)spitch[i] | (uintptr_t)sbatch[i]) % 16 == 0) &&
+                             (((uintptr_t)dst[i] | (uintptr_t)dpitch[i] | (uintptr_t)dbatch[i]) % 8 == 0);
+        if (!aligned || w[i] < 4 || h[i] < 3 || (long long)h[i] * spitch[i] >= 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+        S.src = src[i]; S.dst = dst[i];
+        S.spitch = spitch[i]; S.sbatch = sbatch[i]; S.dpitch = dpitch[i]; S.dbatch = dbatch[i];
+        S.w = w[i]; S.h = h[i]; S.dw = (w[i] + 1) / 2; S.dh = (h[i] + 1) / 2;
+        S.n8 = w[i] / RC::BODY;
+        const int rem = w[i] - S.n8 * RC::BODY;
+        S.rem_nout = (rem == 0) ? 0 : (rem <= RingCfg<4>::BODY ? 4 : 8);
+        S.tiles_x = S.n8 + (rem > 0);
+        S.rows = ring_rows(S.dh, S.tiles_x, batch, resident);
+        S.strips_y = (S.dh + S.rows - 1) / S.rows;
+        S.task_begin = tasks;
+        S.cnt_off = (int)counters;
+        tasks += (long long)S.tiles_x * S.strips_y * batch;
+        if (i + 1 < n_steps) counters += (long long)S.strips_y * batch;
+        if (counters > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    }
+    P.n_steps = n_steps; P.batch = batch; P.n_tasks = tasks;
+    *n_counters = counters;
+    return KLT_OK;
+}
+
+klt_status pyr_fused_launch(const PyrFused& P, cudaStream_t stream)
+{
+    using RC = RingCfg<8>;
+    static PerDeviceOnce configured;
+    const int smem = RC::WARP_BYTES * kWarpsPerBlock;
+    if (configured.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(pyr_build_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (klt_status)e;
+    }
+    const long long blocks = (P.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    pyr_build_fused_kernel<3><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
 }  // namespace klt
