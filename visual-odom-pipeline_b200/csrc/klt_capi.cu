@@ -7,6 +7,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <thread>
+#include <immintrin.h>
 #include <functional>
 #include <mutex>
 #include <new>
@@ -39,6 +43,13 @@ struct klt_ctx {
     // completion counters of the one-launch pyramid build, one array per stream and geometry (klt_pyramid.cu)
     struct PyrScratch { cudaStream_t stream; unsigned* cnt; long long capacity; unsigned gen; long long key[6]; };
     std::vector<PyrScratch> pyr_scratch;
+    // the *_host entry points share the workspaces, streams and events above: one call at a time per context
+    std::mutex host_mutex;
+    // pinned landing zone + helper threads for PAGEABLE host images (see stage_pageable_pair)
+    uint8_t* h_in = nullptr;
+    size_t h_in_bytes = 0;
+    struct Stager;
+    Stager* stager = nullptr;
 };
 
 namespace {
@@ -51,10 +62,32 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Makes the context's device current for the duration of an entry point and restores the caller's device afterwards
+// (a torch process that calls e.g. calcOpticalFlowPyrLK(device=1) keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            changed = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define KLT_DEVICE_GUARD(ctx)                                  \
+    DeviceGuard guard__((ctx)->device);                        \
+    if (guard__.err != cudaSuccess) return (klt_status)guard__.err
+
 klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->d_ws_bytes) return KLT_OK;
-    if (ctx->d_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_ws); ctx->d_ws = nullptr; ctx->d_ws_bytes = 0; }
+    if (ctx->d_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); KLT_CUDA(cudaStreamSynchronize(ctx->stream2)); cudaFree(ctx->d_ws); ctx->d_ws = nullptr; ctx->d_ws_bytes = 0; }
     bytes = align_up(bytes + bytes / 4, 1 << 20);
     cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
@@ -65,7 +98,7 @@ klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
 klt_status ensure_host_ws(klt_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->h_ws_bytes) return KLT_OK;
-    if (ctx->h_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_ws); ctx->h_ws = nullptr; ctx->h_ws_dev = nullptr; ctx->h_ws_bytes = 0; }
+    if (ctx->h_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); KLT_CUDA(cudaStreamSynchronize(ctx->stream2)); cudaFreeHost(ctx->h_ws); ctx->h_ws = nullptr; ctx->h_ws_dev = nullptr; ctx->h_ws_bytes = 0; }
     bytes = align_up(bytes + bytes / 4, 1 << 16);
     cudaError_t e = cudaHostAlloc(&ctx->h_ws, bytes, cudaHostAllocMapped);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
@@ -75,6 +108,130 @@ klt_status ensure_host_ws(klt_ctx* ctx, size_t bytes)
     ctx->h_ws_bytes = bytes;
     return KLT_OK;
 }
+
+}  // namespace
+
+// Helper threads that copy PAGEABLE host images into the context's pinned landing zone, slice by slice, while the DMA
+// engines already move the finished part (the reference hands the drop-in pageable numpy arrays: the output of
+// cv2.bilateralFilter, loader.py:86, and `im.copy()`, pipeline.py:103).  cudaMemcpyAsync from pageable memory makes the
+// driver do the same staging single-threaded and synchronously (measured: +38 us on a KITTI pair); here the copy of a
+// pair is split over the calling thread and kHelpers helpers.  Helpers spin for a short grace period after a job (the
+// reference issues its four calls per frame back to back) and then sleep on a condition variable.
+struct klt_ctx::Stager {
+    static constexpr int kHelpers = 3;
+    static constexpr int kParts = kHelpers + 1;
+    std::thread threads[kHelpers];
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<unsigned> gen{0};
+    std::atomic<int> done[2];
+    bool stop = false;
+    const uint8_t* src[2] = {nullptr, nullptr};
+    uint8_t* dst[2] = {nullptr, nullptr};
+    size_t bytes[2] = {0, 0};
+
+    static void slice(size_t total, int part, size_t& off, size_t& len)
+    {
+        const size_t per = ((total + kParts - 1) / kParts + 63) & ~(size_t)63;
+        off = std::min(total, per * (size_t)part);
+        len = std::min(total - off, per);
+    }
+    void copy_part(int job, int part)
+    {
+        size_t off, len;
+        slice(bytes[job], part, off, len);
+        if (len) std::memcpy(dst[job] + off, src[job] + off, len);
+    }
+    void worker(int part)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            // grace period: poll for ~200 us before sleeping
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spin = 0;; ++spin) {
+                if (gen.load(std::memory_order_acquire) != seen) { got = true; break; }
+                _mm_pause();
+                if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || gen.load(std::memory_order_acquire) != seen; });
+                if (stop) return;
+            }
+            seen = gen.load(std::memory_order_acquire);
+            if (seen == 0xffffffffu) return;
+            copy_part(0, part);
+            done[0].fetch_add(1, std::memory_order_release);
+            copy_part(1, part);
+            done[1].fetch_add(1, std::memory_order_release);
+        }
+    }
+    bool start()
+    {
+        done[0].store(0); done[1].store(0);
+        try {
+            for (int i = 0; i < kHelpers; ++i) threads[i] = std::thread(&Stager::worker, this, i);
+        } catch (...) {
+            shutdown();
+            return false;
+        }
+        return true;
+    }
+    void shutdown()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; gen.store(0xffffffffu, std::memory_order_release); }
+        cv.notify_all();
+        for (auto& t : threads) if (t.joinable()) t.join();
+    }
+    // publish a job of two copies; the caller then runs part kHelpers of each itself and waits with wait_job()
+    void post(const uint8_t* s0, uint8_t* d0, size_t b0, const uint8_t* s1, uint8_t* d1, size_t b1)
+    {
+        src[0] = s0; dst[0] = d0; bytes[0] = b0; src[1] = s1; dst[1] = d1; bytes[1] = b1;
+        done[0].store(0, std::memory_order_relaxed); done[1].store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            unsigned g = gen.load(std::memory_order_relaxed) + 1;
+            if (g == 0 || g == 0xffffffffu) g = 1;
+            gen.store(g, std::memory_order_release);
+        }
+        cv.notify_all();
+    }
+    void finish_job(int job)
+    {
+        copy_part(job, kHelpers);
+        while (done[job].load(std::memory_order_acquire) < kHelpers) _mm_pause();
+    }
+};
+
+namespace {
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    const cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+klt_status ensure_host_in(klt_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_in_bytes) return KLT_OK;
+    if (ctx->h_in) {
+        KLT_CUDA(cudaStreamSynchronize(ctx->stream));
+        KLT_CUDA(cudaStreamSynchronize(ctx->stream2));
+        cudaFreeHost(ctx->h_in); ctx->h_in = nullptr; ctx->h_in_bytes = 0;
+    }
+    bytes = align_up(bytes + bytes / 4, 1 << 16);
+    cudaError_t e = cudaHostAlloc(&ctx->h_in, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    ctx->h_in_bytes = bytes;
+    return KLT_OK;
+}
+
+}  // namespace
+
+namespace {
 
 // Attaches the stream's work list to a launch and picks the hand-off parameters.  The list is sized for the worst case
 // (every point handed off); its control words are zeroed once here and re-zeroed by the kernel at the end of each launch.
@@ -284,7 +441,8 @@ klt_status klt_create(int device, klt_ctx** out)
     cudaDeviceProp prop;
     KLT_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return KLT_ERR_NO_DEVICE;  // the fatbin holds sm_100a SASS only
-    KLT_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return (klt_status)guard.err;
     klt_ctx* ctx = new (std::nothrow) klt_ctx();
     if (!ctx) return KLT_ERR_OUT_OF_MEMORY;
     ctx->device = device;
@@ -310,12 +468,14 @@ klt_status klt_create(int device, klt_ctx** out)
 klt_status klt_destroy(klt_ctx* ctx)
 {
     if (!ctx) return KLT_OK;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->stager) { ctx->stager->shutdown(); delete ctx->stager; ctx->stager = nullptr; }
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->h_ws) cudaFreeHost(ctx->h_ws);
+    if (ctx->h_in) cudaFreeHost(ctx->h_in);
     cudaDeviceSynchronize();   // caller streams that used the work lists may be gone already
     for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
     for (auto& sc : ctx->lk_scratch) {
@@ -386,6 +546,7 @@ klt_status klt_pyr_down(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_
                         uint8_t* d_dst, int64_t dst_pitch, int64_t dst_batch_stride, int batch, void* stream)
 {
     if (!ctx) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     return pyr_down_launch(d_src, w, h, src_pitch, src_batch_stride, d_dst, dst_pitch, dst_batch_stride, batch,
                            ctx->sm_count, (cudaStream_t)stream);
 }
@@ -394,6 +555,7 @@ klt_status klt_pyr_build(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layou
                          int first_item, int n_items, void* stream)
 {
     if (!ctx || !d_img) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     klt_status s = check_layout(layout);
     if (s != KLT_OK) return s;
     if (layout->top > 0 && !d_pyr) return KLT_ERR_INVALID_ARG;
@@ -434,6 +596,7 @@ klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* 
                         int32_t* d_iters, int n_per_pair, const klt_lk_params* params, void* stream)
 {
     if (!ctx || !params || !d_prev_img || !d_next_img || n_per_pair < 0 || n_pairs < 0) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     klt_status s = check_layout(layout);
     if (s != KLT_OK) return s;
     if (pair_stride < 1 || prev_first < 0 || next_first < 0) return KLT_ERR_INVALID_ARG;
@@ -475,7 +638,8 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     if (!ctx || !params || !prev_img || !next_img || w <= 0 || h <= 0 || n < 0 || max_level < 0) return KLT_ERR_INVALID_ARG;
     if (prev_pitch < w || next_pitch < w) return KLT_ERR_INVALID_ARG;
     if (n > 0 && (!prev_pts || !next_pts || !status || !err)) return KLT_ERR_INVALID_ARG;
-    KLT_CUDA(cudaSetDevice(ctx->device));
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
     // both images form a batch of 2 so that every pyramid level is ONE launch for the pair
     klt_pyr_layout lay;
     klt_status s = klt_pyr_plan(w, h, params->win_w, params->win_h, max_level, 2, &lay);
@@ -517,10 +681,36 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     static const bool one_stream = getenv("KLT_ONE_COPY_STREAM") != nullptr;   // A/B runs
     cudaStream_t st2 = one_stream ? st : ctx->stream2;
     if (linear) {
-        KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, next_img, raw_next, cudaMemcpyHostToDevice, st2));
+        // Pageable inputs (what the un-edited reference passes) are staged through the context's pinned landing zone by
+        // the calling thread and the helper threads; the DMA of the next image runs while the previous image is staged.
+        static const bool no_stager = getenv("KLT_NO_STAGER") != nullptr;   // A/B runs: let the driver stage pageable memory
+        const uint8_t* src_next = next_img;
+        const uint8_t* src_prev = prev_img;
+        const float* src_pts = prev_pts;
+        bool staged = false;
+        if (!no_stager && raw_prev + raw_next >= (256u << 10) && (is_pageable(prev_img) || is_pageable(next_img))) {
+            const size_t in_slot = align_up(std::max(raw_prev, raw_next), 256);
+            const size_t in_pts = align_up((size_t)n * 8, 256);
+            s = ensure_host_in(ctx, 2 * in_slot + in_pts);
+            if (s != KLT_OK) return s;
+            if (!ctx->stager) {
+                ctx->stager = new (std::nothrow) klt_ctx::Stager();
+                if (ctx->stager && !ctx->stager->start()) { delete ctx->stager; ctx->stager = nullptr; }
+            }
+            if (ctx->stager) {
+                ctx->stager->post(next_img, ctx->h_in, raw_next, prev_img, ctx->h_in + in_slot, raw_prev);
+                std::memcpy(ctx->h_in + 2 * in_slot, prev_pts, (size_t)n * 8);
+                src_next = ctx->h_in; src_prev = ctx->h_in + in_slot;
+                src_pts = reinterpret_cast<const float*>(ctx->h_in + 2 * in_slot);
+                staged = true;
+            }
+        }
+        if (staged) ctx->stager->finish_job(0);
+        KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, src_next, raw_next, cudaMemcpyHostToDevice, st2));
         if (st2 != st) KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
-        KLT_CUDA(cudaMemcpyAsync(d + off_pts, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        KLT_CUDA(cudaMemcpyAsync(d + off_raw, prev_img, raw_prev, cudaMemcpyHostToDevice, st));
+        KLT_CUDA(cudaMemcpyAsync(d + off_pts, src_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        if (staged) ctx->stager->finish_job(1);
+        KLT_CUDA(cudaMemcpyAsync(d + off_raw, src_prev, raw_prev, cudaMemcpyHostToDevice, st));
         if (st2 != st) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
         if (prev_pitch == next_pitch) {
             s = repitch_launch(d + off_raw, prev_pitch, (long long)raw_slot, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 2, st);
@@ -634,6 +824,7 @@ klt_status klt_track_filter(klt_ctx* ctx, const float* d_p0, const float* d_p1, 
                             float max_bidir_error, int w, int h, uint8_t* d_keep, float* d_bidir_err, void* stream)
 {
     if (!ctx) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     return track_filter_launch(d_p0, d_p1, d_p0r, (long long)n, max_bidir_error, w, h, d_keep, d_bidir_err, (cudaStream_t)stream);
 }
 
@@ -654,7 +845,8 @@ klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img,
     if (level_offsets) level_offsets[lay.top + 1] = off;
     if (!out) return KLT_OK;
     if (!img || pitch < w) return KLT_ERR_INVALID_ARG;
-    KLT_CUDA(cudaSetDevice(ctx->device));
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
     const size_t ipitch = align_up((size_t)w, 128);
     const size_t ibytes = align_up(ipitch * (size_t)h, 256);
     lay.level[0].pitch = (int64_t)ipitch;
@@ -694,6 +886,7 @@ klt_status klt_corner_min_eigen_val(klt_ctx* ctx, const uint8_t* d_img, int w, i
     if (w < 1 || h < 1 || batch < 1 || block_size < 1) return KLT_ERR_INVALID_ARG;
     if (ws_bytes < (int64_t)corners_ws_bytes(w, h, batch) || ((uintptr_t)d_ws & 255)) return KLT_ERR_INVALID_ARG;
     if (d_mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     return corner_min_eig_launch(d_img, pitch, batch_stride, w, h, batch, block_size, d_eig, eig_pitch, eig_batch_stride,
                                  d_mask, mask_pitch, mask_batch_stride, d_max, d_ws, (cudaStream_t)stream);
 }
@@ -705,6 +898,7 @@ klt_status klt_corner_candidates(klt_ctx* ctx, const float* d_eig, int64_t eig_p
 {
     if (!ctx || !d_eig || !d_max || !d_keys || !d_count || eig_pitch < w) return KLT_ERR_INVALID_ARG;
     if (d_mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     return corner_candidates_launch(d_eig, eig_pitch, eig_batch_stride, w, h, batch, d_mask, mask_pitch, mask_batch_stride,
                                     d_max, quality_level, reinterpret_cast<unsigned long long*>(d_keys), keys_batch_stride,
                                     capacity, d_count, (cudaStream_t)stream);
@@ -779,7 +973,7 @@ static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, in
             // corners are >= minDistance apart and a cell is at most minDistance + 0.5 wide, so 4 is never exceeded (checked).
             // A candidate first reads the 3 x 3 counters (three 3-byte reads); most candidates have empty neighbourhoods
             // late in the list or find their conflict in the first occupied cell.
-            struct Cell { short x[4], y[4]; };
+            struct Cell { unsigned short x[4], y[4]; };   // keys carry 16-bit unsigned coordinates (w, h <= 65535)
             const int gw2 = gw + 2;
             const size_t ncell = (size_t)gw2 * (gh + 2);
             thread_local std::vector<unsigned char> cnt_buf;
@@ -803,7 +997,7 @@ static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, in
                         const int m = cnt[row + rx];
                         const Cell& cl = cells[row + rx];
                         for (int j = 0; j < m; ++j) {
-                            const long long dx = x - cl.x[j], dy = y - cl.y[j];
+                            const long long dx = x - (int)cl.x[j], dy = y - (int)cl.y[j];
                             if (dx * dx + dy * dy < md2i) { good = false; break; }
                         }
                     }
@@ -811,7 +1005,7 @@ static klt_status select_corners(uint64_t* keys, int64_t n_keys, bool sorted, in
                 if (!good) continue;
                 const size_t cc = c0 + gw2 + 1;
                 if (cnt[cc] >= 4) return KLT_ERR_INTERNAL;
-                cells[cc].x[cnt[cc]] = (short)x; cells[cc].y[cnt[cc]] = (short)y; ++cnt[cc];
+                cells[cc].x[cnt[cc]] = (unsigned short)x; cells[cc].y[cnt[cc]] = (unsigned short)y; ++cnt[cc];
                 if (emit(x, y)) break;
             }
             *n_out = nc;
@@ -885,7 +1079,8 @@ klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64
 {
     if (!ctx || !img || !eig || w < 1 || h < 1 || pitch < w || block_size < 1) return KLT_ERR_INVALID_ARG;
     if (block_size / 2 >= w || block_size / 2 >= h) return KLT_ERR_UNSUPPORTED;
-    KLT_CUDA(cudaSetDevice(ctx->device));
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
     const size_t img_bytes = upload_bytes(pitch, w, h);
     const size_t eig_bytes = align_up((size_t)w * h * 4, 256);
     const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
@@ -919,7 +1114,8 @@ static klt_status gftt_host_impl(klt_ctx* ctx, const uint8_t* img, int64_t pitch
     if (mask && mask_pitch < w) return KLT_ERR_INVALID_ARG;
     if (block_size / 2 >= w || block_size / 2 >= h || w > 65535 || h > 65535) return KLT_ERR_UNSUPPORTED;
     *n_out = 0;
-    KLT_CUDA(cudaSetDevice(ctx->device));
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
     const size_t img_bytes = upload_bytes(pitch, w, h);
     const size_t pts_bytes = from_points ? align_up((size_t)n_points * 8 + 8, 256) : 0;
     const size_t mask_bytes = mask ? upload_bytes(mask_pitch, w, h) : (from_points ? align_up((size_t)w * h, 256) + pts_bytes : 0);
@@ -1054,6 +1250,7 @@ klt_status klt_corner_mask_from_points(klt_ctx* ctx, const float* d_points, int 
                                        int64_t mask_pitch, void* stream)
 {
     if (!ctx) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
     return corner_mask_from_points_launch(d_points, n, radius, w, h, d_mask, mask_pitch, (cudaStream_t)stream);
 }
 
