@@ -1,6 +1,6 @@
-"""Run in a fresh process with KLT_LK_* set (the library reads them once): the opt-in LK variants -- hand-off of long
-points to the long-point kernel (KLT_LK_BUDGET), one-warp-per-point bulk shape (KLT_LK_SHAPE=warp) -- must stay
-bit-identical to live cv2.  Used by tests/test_gpu_parity.py::test_lk_optin_variants_bit_exact."""
+"""Run in a fresh process with KLT_LK_WPP set (the library reads it once): every team size of the specialised LK kernel
+(1, 2 or 4 warps per keypoint; the default picks by window and point count) must stay
+bit-identical to live cv2.  Used by tests/test_gpu_parity.py::test_lk_team_sizes_bit_exact."""
 import os
 import sys
 
@@ -19,7 +19,7 @@ CASES = [
     (120, 160, 96, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 5, {}),
 ]
 bad = 0
-for rep in range(2):      # twice: the first call of a process also allocates the work list
+for rep in range(2):
     for h, w, n, win, lvl, crit, motion, margin, kw in CASES:
         a, b = S.frame_pair(h, w, seed=7 + rep, motion=motion, **kw)
         p = S.uniform_points(n, h, w, seed=3 + rep, margin=margin)

@@ -149,15 +149,13 @@ def test_lk_bit_exact_vs_oracle_and_cv2(klt, oracle, cv2, case):
     assert_lk_equal(got, ref, "vs cv2")
 
 
-@pytest.mark.parametrize("env", [{"KLT_LK_BUDGET": "7"}, {"KLT_LK_BUDGET": "3", "KLT_LK_RESUME_BLOCKS": "5"}, {"KLT_LK_BUDGET": "7", "KLT_LK_SERIAL": "1"},
-                                 {"KLT_LK_SHAPE": "warp"}, {"KLT_LK_SHAPE": "warp", "KLT_LK_BUDGET": "6"}, {"KLT_LK_SHAPE": "warp", "KLT_LK_BUDGET": "-1"}],
-                         ids=["handoff", "handoff_few_ctas", "handoff_serial", "warp", "warp_budget", "warp_in_warp_replay"])
-def test_lk_optin_variants_bit_exact(klt, env):
-    """The opt-in LK variants (long points handed to lk_long_kernel beside a two-phase bulk launch; the
-    one-warp-per-point bulk shape) are not the default path, but they ship in the library: same bit-exactness bar."""
+@pytest.mark.parametrize("wpp", ["1", "2", "4"])
+def test_lk_team_sizes_bit_exact(klt, wpp):
+    """Every team size of the specialised kernel (leader warp + 0, 1 or 3 follower warps per keypoint) ships in the
+    library and is picked by window / point count: same bit-exactness bar for each, forced through KLT_LK_WPP."""
     import os, subprocess, sys
     e = dict(os.environ)
-    e.update(env)
+    e["KLT_LK_WPP"] = wpp
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lk_variant_check.py")], env=e,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -35,10 +35,6 @@ struct klt_ctx {
     uint8_t* h_ws = nullptr;
     uint8_t* h_ws_dev = nullptr;   // device-side alias of h_ws
     size_t h_ws_bytes = 0;
-    // LK work lists (long points handed from the bulk shape to resume teams, klt_lk_fast.cu): one per stream that has
-    // launched LK through this context, so that launches on different streams never share one
-    struct LKScratch { cudaStream_t stream; int* ctrl; int* nl; LKResume* wl; long long capacity; cudaStream_t side; cudaEvent_t ev_fork, ev_join; int epoch; };
-    std::vector<LKScratch> lk_scratch;
     std::mutex lk_mutex;
     // completion counters of the one-launch pyramid build, one array per stream and geometry (klt_pyramid.cu)
     struct PyrScratch { cudaStream_t stream; unsigned* cnt; long long capacity; unsigned gen; long long key[6]; };
@@ -233,80 +229,6 @@ klt_status ensure_host_in(klt_ctx* ctx, size_t bytes)
 
 namespace {
 
-// Attaches the stream's work list to a launch and picks the hand-off parameters.  The list is sized for the worst case
-// (every point handed off); its control words are zeroed once here and re-zeroed by the kernel at the end of each launch.
-klt_status attach_lk_scratch(klt_ctx* ctx, cudaStream_t stream, LKLaunch& L)
-{
-    L.wl = nullptr; L.wl_ctrl = nullptr; L.nl = nullptr; L.budget = 0; L.n_resume_blocks = 0; L.n_bulk_blocks = 0;
-    L.two_phase = 0; L.suspect_margin = 0.f; L.epoch = 0; L.side_stream = nullptr; L.ev_fork = nullptr; L.ev_join = nullptr;
-    // The hand-off of long points is OFF by default (KLT_LK_BUDGET=7 enables it): measured on B200 over the 155 point sets
-    // of bench.py it shortens the pairs with a bad tail (106 -> 87 us kernel span on the profiling pair) but not the
-    // mean (116.7 -> 119.2 us), DESIGN.md s7.  KLT_LK_SHAPE=warp (one warp per point) needs a work list for the
-    // iterations whose float32 sums really round, so it gets one with budget 0 unless told otherwise.
-    static const char* env_budget = getenv("KLT_LK_BUDGET");
-    static const char* env_resume = getenv("KLT_LK_RESUME_BLOCKS");
-    static const char* env_shape = getenv("KLT_LK_SHAPE");
-    int budget = env_budget ? atoi(env_budget) : ((env_shape && env_shape[0] == 'w') ? 0 : -1);
-    const long long total = (long long)L.n_per_pair * L.batch;
-    if (budget < 0 || total <= 0) return KLT_OK;          // KLT_LK_BUDGET=-1: no work list at all
-    // The iteration budget is for the latency shape only: once the points fill the chip several times over, the long
-    // points overlap with the rest of the launch and the hand-off would only repeat their patch pass.  Iterations whose
-    // float32 sums really round are handed over at any size (budget 0: only those).
-    if (total > (long long)ctx->sm_count * 64) budget = 0;
-    std::lock_guard<std::mutex> guard(ctx->lk_mutex);
-    klt_ctx::LKScratch* slot = nullptr;
-    for (auto& sc : ctx->lk_scratch)
-        if (sc.stream == stream) { slot = &sc; break; }
-    if (!slot) {
-        klt_ctx::LKScratch fresh = {stream, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0};
-        // the long-point kernel runs beside the bulk kernel on its own stream (fork / join with two events)
-        // Highest priority: its CTAs (one per SM) take the first slots the bulk kernel frees, whichever grid the
-        // hardware started first.
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        cudaError_t e = cudaStreamCreateWithPriority(&fresh.side, cudaStreamNonBlocking, prio_hi);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fresh.ev_fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fresh.ev_join, cudaEventDisableTiming);
-        if (e != cudaSuccess) {
-            if (fresh.side) cudaStreamDestroy(fresh.side);
-            if (fresh.ev_fork) cudaEventDestroy(fresh.ev_fork);
-            return (klt_status)e;
-        }
-        try { ctx->lk_scratch.push_back(fresh); } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
-        slot = &ctx->lk_scratch.back();
-    }
-    if (slot->capacity < total) {
-        // a launch on this stream may still be using the old list
-        if (slot->ctrl) { KLT_CUDA(cudaStreamSynchronize(stream)); cudaFree(slot->ctrl); slot->ctrl = nullptr; slot->wl = nullptr; slot->capacity = 0; }
-        const long long cap = (total + total / 4 + 256 + 3) / 4 * 4;
-        void* p = nullptr;
-        const size_t bytes = 256 + (size_t)cap * (sizeof(LKResume) + sizeof(int));
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
-        e = cudaMemset(p, 0, bytes);   // control words and the epoch words of the entries
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the memset is not ordered with the (non-blocking) streams that use the list
-        if (e != cudaSuccess) { cudaFree(p); return (klt_status)e; }
-        slot->ctrl = static_cast<int*>(p);
-        slot->wl = reinterpret_cast<LKResume*>(static_cast<uint8_t*>(p) + 256);
-        slot->nl = reinterpret_cast<int*>(static_cast<uint8_t*>(p) + 256 + (size_t)cap * sizeof(LKResume));
-        slot->capacity = cap;
-    }
-    L.wl = slot->wl; L.wl_ctrl = slot->ctrl; L.nl = slot->nl; L.budget = budget;
-    slot->epoch = (slot->epoch % 0x3fffffff) + 1;   // never 0: fresh device memory reads as epoch 0
-    L.epoch = slot->epoch;
-    L.n_resume_blocks = env_resume ? atoi(env_resume) : ctx->sm_count;
-    static const char* env_serial = getenv("KLT_LK_SERIAL");   // A/B runs: long-point kernel behind the bulk kernel, one phase
-    if (budget > 0 && total < (1LL << 30) && !(env_serial && env_serial[0] == '1')) {
-        L.two_phase = 1;
-        L.suspect_margin = 0.5f * (float)(L.win_w > L.win_h ? L.win_w : L.win_h) + 16.f;
-        L.side_stream = slot->side; L.ev_fork = slot->ev_fork; L.ev_join = slot->ev_join;
-        // CTAs of the long-point kernel: each holds a slot of the bulk kernel while it waits for work (measured on a
-        // KITTI pair: 48 .. 74 CTAs equal, 148 and more slow the bulk down)
-        if (!env_resume) L.n_resume_blocks = ctx->sm_count / 2;
-    }
-    return KLT_OK;
-}
-
 // All levels of the item range in ONE launch (pyr_build_fused_kernel); KLT_ERR_UNSUPPORTED: launch level by level.
 klt_status pyr_build_one_launch(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* lay, uint8_t* d_pyr, int first_item,
                                 int n_items, cudaStream_t stream)
@@ -478,12 +400,6 @@ klt_status klt_destroy(klt_ctx* ctx)
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     cudaDeviceSynchronize();   // caller streams that used the work lists may be gone already
     for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
-    for (auto& sc : ctx->lk_scratch) {
-        if (sc.ctrl) cudaFree(sc.ctrl);
-        if (sc.side) cudaStreamDestroy(sc.side);
-        if (sc.ev_fork) cudaEventDestroy(sc.ev_fork);
-        if (sc.ev_join) cudaEventDestroy(sc.ev_join);
-    }
     delete ctx;
     return KLT_OK;
 }
@@ -618,8 +534,6 @@ klt_status klt_lk_track(klt_ctx* ctx, const uint8_t* d_prev_img, const uint8_t* 
     set_eps_brackets(L);
     L.flags = params->flags;
     L.min_eig_thr = (float)params->min_eig_threshold;
-    s = attach_lk_scratch(ctx, (cudaStream_t)stream, L);
-    if (s != KLT_OK) return s;
     return lk_launch(L, ctx->sm_count, (cudaStream_t)stream);
 }
 
@@ -759,8 +673,6 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     set_eps_brackets(L);
     L.flags = params->flags;
     L.min_eig_thr = (float)params->min_eig_threshold;
-    s = attach_lk_scratch(ctx, st, L);
-    if (s != KLT_OK) return s;
     s = lk_launch(L, ctx->sm_count, st);
     if (s != KLT_OK) return s;
     if (bidir) {

@@ -90,33 +90,7 @@ klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0
 klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
                           long long dbatch, int w, int h, int n_img, cudaStream_t stream);
 
-// A point that exceeded the per-level iteration budget of the bulk shape: where a resume team picks it up.
-struct LKResume {
-    long long gid;         // point index in the launch
-    int level, j;          // pyramid level and the iteration about to start
-    float nx, ny;          // window origin in the next image at that iteration (centre - half window)
-    float pdx, pdy;        // previous update (oscillation test)
-    int iters, pad[3];     // iterations counted so far
-};
-static_assert(sizeof(LKResume) == 48, "work-list entries are read as 3 x int4");
-
-// words of LKLaunch::wl_ctrl (zero between launches: the long-point kernel's last CTA resets them)
-enum { kCtrlPushed = 0, kCtrlLongGone = 1, kCtrlNormal = 2, kCtrlDecided = 3, kCtrlFinished = 4 };
-
 struct LKLaunch {
-    // work list of the long points (klt_lk_fast.cu); wl == nullptr: no hand-off
-    LKResume* wl;
-    int* wl_ctrl;
-    int* nl;               // two-phase bulk launch: indices of the points that are not border suspects
-    int budget;            // iterations per level before a point is handed off
-    int n_resume_blocks;   // CTAs of the long-point kernel
-    int two_phase;         // bulk grid = [suspects first | everything else], long-point kernel concurrent on side_stream
-    float suspect_margin;  // a point closer than this to the image border (level 0) is a suspect
-    int epoch;             // launch counter of the scratch: marks the work-list entries of THIS launch as complete
-    long long n_bulk_blocks;
-    void* side_stream;     // host only: cudaStream_t / cudaEvent_t of the context (fork / join around the long-point kernel)
-    void* ev_fork;
-    void* ev_join;
     PyrView prev, next;
     const float* prev_pts;
     float* next_pts;
@@ -136,25 +110,10 @@ struct LKLaunch {
     float min_eig_thr;
 };
 
-#ifdef __CUDACC__
-// Work-list entry: the payload first, then (after a fence) the word that carries the launch epoch -- the consumer may
-// already have seen the incremented counter, so it waits for this word before it reads the payload.
-__device__ __forceinline__ void push_entry(const LKLaunch& L, int slot, long long gid, int level, int j, float nx, float ny,
-                                           float pdx, float pdy, int iters)
-{
-    int4* dst = reinterpret_cast<int4*>(L.wl + slot);
-    __stcg(dst, make_int4((int)(unsigned)(gid & 0xffffffffLL), (int)(gid >> 32), level, j));
-    __stcg(dst + 1, make_int4(__float_as_int(nx), __float_as_int(ny), __float_as_int(pdx), __float_as_int(pdy)));
-    __threadfence();
-    __stcg(dst + 2, make_int4(iters, 0, 0, L.epoch));
-}
-#endif
-
 klt_status lk_launch(const LKLaunch& L, int sm_count, cudaStream_t stream);
 klt_status track_filter_launch(const float* p0, const float* p1, const float* p0r, long long n, float max_bidir_error,
                                int w, int h, uint8_t* keep, float* bidir, cudaStream_t stream);
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream);
-klt_status lk_launch_warp(const LKLaunch& L, cudaStream_t stream);   // bulk shape, one warp per point (klt_lk_warp.cu)
 klt_status lk_init(int device);
 
 // Shi-Tomasi detection (klt_corners.cu)

@@ -2,18 +2,24 @@
 //
 // Same arithmetic as klt_lk.cu (bit-exact with cv2.calcOpticalFlowPyrLK as called
 // at reference src/extractor/extractor.py:44,45,65,66); this variant is what the BASELINE configs
-// (winSize 21 and 31) run.  Differences in structure:
-//  * WPP in {1,2,4} warps cooperate on one keypoint (named barriers), so a 2000-point frame pair fills
-//    the chip and the per-iteration latency of the slowest point -- which bounds the launch -- drops;
-//    WPP = 1 is the throughput shape for large batches.
+// (winSize 21 and 31) run.  Structure:
+//  * a team of WPP in {1,2,4} warps tracks one keypoint through all pyramid levels in one launch;
+//  * LEADER / FOLLOWERS: everything that is scalar per point (window position, range tests, Q14 weights, the 2x2
+//    solve, the termination tests, the exactness tests of the float32 sums) is executed by warp 0 of the team only.
+//    It drives the other warps with COMMANDS through an 8-word mailbox in shared memory (level setup, iteration,
+//    class sums, serial replay, err pass); the followers execute the per-pixel part of a command, leave their partial
+//    sums in shared memory and wait for the next command.  Two named barriers per point couple the two sides
+//    (command: leader arrives / followers wait; partials: followers arrive / leader waits), so nobody blocks longer
+//    than it has to.  In round 1 every warp of the team executed the scalar part redundantly: 9.3 thread-instructions
+//    per algorithmic MAC, 75 % of them outside the per-pixel loops (profiles/r01);
 //  * the window is cut into 4-pixel units; each thread keeps the Q5 intensity / Q14 derivative patch of
 //    its units in registers for the whole level, only the next-image region lives in shared memory;
 //  * bilinear taps use dp2a (two 14-bit weights x two u8 pixels per instruction, exact);
 //  * neighbourhoods are staged with 32-bit loads (all loads in flight before the first store);
-//  * the mismatch sums are reduced in three tiers: (0) if sum|d|*max(|gx|,|gy|) over the WHOLE window
-//    is <= 2^24 every float32 partial sum OpenCV forms is an exact integer, so b = float(sum) and only
-//    3 values cross the warp(s); (1) otherwise per-accumulation-class sums (4 SIMD lanes + tail) with
-//    the same test per class; (2) otherwise a serial float32 replay in OpenCV's order.
+//  * the mismatch sums are reduced in three tiers: (0) if sum|d*gx| and sum|d*gy| over the WHOLE window are
+//    <= 2^24 every float32 partial sum OpenCV forms is an exact integer, so b = float(sum) and only 4 values cross
+//    the warps; (1) otherwise per-accumulation-class sums (4 SIMD lanes + tail) with a bound per class; (2) otherwise
+//    a serial float32 replay in OpenCV's order.
 #include "klt_common.cuh"
 
 #include <cstdlib>
@@ -79,11 +85,10 @@ struct Cfg {
     static constexpr int OFF_I = OFF_D + D_BYTES;             // ireg
     static constexpr int I_BYTES = r16(SI * IR);
     static constexpr int NS = NV / 8;                         // 8-pixel SIMD steps per window row
-    static constexpr int OFF_R3 = OFF_I + I_BYTES;            // [2][WPP] int4
-    static constexpr int OFF_R16 = OFF_R3 + 2 * WPP * 16;     // [2][16 values][4 warps] int
-    static constexpr int OFF_GID = OFF_R16 + 2 * 256;         // the point's index (long long), parked here by thread 0 so
-                                                              // that it does not occupy two registers for the whole point
-    static constexpr int POINT_BYTES = (OFF_GID + 16 + 127) / 128 * 128;
+    static constexpr int OFF_R3 = OFF_I + I_BYTES;            // [4 warps] int4: partial sums of a command
+    static constexpr int OFF_R16 = OFF_R3 + 4 * 16;           // [16 values][4 warps] int: class sums of a command
+    static constexpr int OFF_CMD = OFF_R16 + 256;             // mailbox: 2 x int4
+    static constexpr int POINT_BYTES = (OFF_CMD + 32 + 127) / 128 * 128;
 };
 
 __device__ __forceinline__ int dp2a_lo(uint32_t w, uint32_t b, int c)
@@ -98,33 +103,33 @@ __device__ __forceinline__ int dp2a_hi(uint32_t w, uint32_t b, int c)
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c));
     return d;
 }
+#ifdef KLT_LK_TIMELINE
 __device__ __forceinline__ unsigned long long gtimer()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
 
-// Per-pixel patch state of one window pixel: Q5 intensity, Q14 derivative (gx, gy), gm = max(|gx|,|gy|).
-// Plain registers when a thread owns few pixels, two packed registers per pixel otherwise.
+// Per-pixel patch state of one window pixel: Q5 intensity, Q14 derivative (gx, gy).
+// Plain registers when a thread owns few pixels, two registers per pixel otherwise.
 template <bool PACK> struct PxStore;
 template <> struct PxStore<false> {
-    int iv_, gx_, gy_, gm_;
-    __device__ __forceinline__ void set(int iv, int gx, int gy, int gm) { iv_ = iv; gx_ = gx; gy_ = gy; gm_ = gm; }
+    int iv_, gx_, gy_;
+    __device__ __forceinline__ void set(int iv, int gx, int gy) { iv_ = iv; gx_ = gx; gy_ = gy; }
     __device__ __forceinline__ int iv() const { return iv_; }
     __device__ __forceinline__ int gx() const { return gx_; }
     __device__ __forceinline__ int gy() const { return gy_; }
-    __device__ __forceinline__ int gm() const { return gm_; }
 };
 template <> struct PxStore<true> {
-    uint32_t a_, g_;
-    __device__ __forceinline__ void set(int iv, int gx, int gy, int gm) { a_ = (uint32_t)iv | ((uint32_t)gm << 16); g_ = ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16); }
-    __device__ __forceinline__ int iv() const { return (int)(a_ & 0xffffu); }
+    int a_; uint32_t g_;
+    __device__ __forceinline__ void set(int iv, int gx, int gy) { a_ = iv; g_ = ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16); }
+    __device__ __forceinline__ int iv() const { return a_; }
     __device__ __forceinline__ int gx() const { return (int)(short)(g_ & 0xffffu); }
     __device__ __forceinline__ int gy() const { return ((int)g_) >> 16; }
-    __device__ __forceinline__ int gm() const { return (int)(a_ >> 16); }
 };
 // the 4 mismatch values of one unit
 template <bool PACK> struct DiffStore;
@@ -139,11 +144,19 @@ template <> struct DiffStore<true> {
     __device__ __forceinline__ int get(int j) const { return (j & 1) ? (((int)p_[j >> 1]) >> 16) : (int)(short)(p_[j >> 1] & 0xffffu); }
 };
 
+// full barrier over the team (all WPP warps wait)
 template <int WPP>
-__device__ __forceinline__ void point_sync(int bar)
+__device__ __forceinline__ void team_sync(int bar)
 {
     if constexpr (WPP == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(32 * WPP) : "memory");
+}
+// one-sided use of a named barrier: the producers of a hand-over arrive (and run on), the consumers wait
+template <int WPP>
+__device__ __forceinline__ void team_arrive(int bar)
+{
+    if constexpr (WPP == 1) __syncwarp();
+    else asm volatile("bar.arrive %0, %1;" ::"r"(bar), "n"(32 * WPP) : "memory");
 }
 
 __device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
@@ -215,49 +228,6 @@ __device__ __forceinline__ void load5(const uint8_t* row, int o, uint32_t& a, ui
     b = __funnelshift_rc(w0, w1, s + 8);
 }
 
-// sum 3 values over all threads of the point; every thread gets the totals (REDUX + one smem exchange)
-template <int WPP>
-__device__ __forceinline__ void point_sum3(int& a, int& b, int& c, int4* red3, int& par3, int wip, int lane, int bar)
-{
-    a = __reduce_add_sync(kFull, a);
-    b = __reduce_add_sync(kFull, b);
-    c = __reduce_add_sync(kFull, c);
-    if constexpr (WPP > 1) {
-        int4* slot = red3 + par3 * WPP;
-        if (lane == 0) slot[wip] = make_int4(a, b, c, 0);
-        point_sync<WPP>(bar);
-        a = 0; b = 0; c = 0;
-#pragma unroll
-        for (int w = 0; w < WPP; ++w) {
-            const int4 v = slot[w];
-            a += v.x; b += v.y; c += v.z;
-        }
-        par3 ^= 1;
-    }
-}
-
-// Sum 15 values over all threads of the point.  Returns, in lane L < 15 of EVERY warp, the point-wide total of
-// value L (one REDUX per value, then one value-major smem exchange so a lane fetches its partials with one load).
-template <int WPP>
-__device__ __forceinline__ int point_sum15_lane(const int (&v)[16], int* red16, int& par16, int wip, int lane, int bar)
-{
-    int mine = 0;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) {
-        const int t = __reduce_add_sync(kFull, v[i]);
-        mine = (lane == i) ? t : mine;
-    }
-    if constexpr (WPP > 1) {
-        int* slot = red16 + par16 * 64;
-        if (lane < 15) slot[lane * 4 + wip] = mine;
-        point_sync<WPP>(bar);
-        const int4 t = reinterpret_cast<const int4*>(slot)[lane & 15];
-        mine = t.x + t.y + (WPP > 2 ? t.z + t.w : 0);
-        par16 ^= 1;
-    }
-    return mine;
-}
-
 // serial float32 sum of one zero-padded chain of n4 floats (n4 % 4 == 0), in order
 __device__ __forceinline__ float chain_sum(const float* __restrict__ p, int n4)
 {
@@ -300,62 +270,6 @@ __device__ __forceinline__ void zero_pad_b(int* buf, int tid)
     if (tid < 8 * SPAD) buf[(tid / (SPAD > 0 ? SPAD : 1)) * CH::SLEN + CH::SUSED + tid % (SPAD > 0 ? SPAD : 1)] = 0;
 }
 
-// The same replay for the resume teams, which have the registers to keep the loads ahead of the adds: the chain is then
-// bound by the dependent float adds alone (4 cycles each) instead of a shared-memory round trip per group of four.
-template <int N4>
-__device__ __forceinline__ float chain_sum_f4(const float4* __restrict__ src)
-{
-    constexpr int G = 8;
-    float4 cur[G], nxt[G];
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < G; ++i) cur[i] = (i < N4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < N4; c += G) {
-#pragma unroll
-        for (int i = 0; i < G; ++i) nxt[i] = (c + G + i < N4) ? src[c + G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < G; ++i)
-            if (c + i < N4) acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, cur[i].x), cur[i].y), cur[i].z), cur[i].w);
-#pragma unroll
-        for (int i = 0; i < G; ++i) cur[i] = nxt[i];
-    }
-    return acc;
-}
-template <int N4>
-__device__ __forceinline__ float chain_sum_i4(const int4* __restrict__ src)
-{
-    constexpr int G = 8;
-    int4 cur[G], nxt[G];
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < G; ++i) cur[i] = (i < N4) ? src[i] : make_int4(0, 0, 0, 0);
-#pragma unroll
-    for (int c = 0; c < N4; c += G) {
-#pragma unroll
-        for (int i = 0; i < G; ++i) nxt[i] = (c + G + i < N4) ? src[c + G + i] : make_int4(0, 0, 0, 0);
-#pragma unroll
-        for (int i = 0; i < G; ++i)
-            if (c + i < N4) acc = __fadd_rn(__fadd_rn(acc, (float)(cur[i].x + cur[i].y)), (float)(cur[i].z + cur[i].w));
-#pragma unroll
-        for (int i = 0; i < G; ++i) cur[i] = nxt[i];
-    }
-    return acc;
-}
-template <int WW, int WH>
-__device__ __forceinline__ void replay_b_long(int* __restrict__ buf, int wip, int lane)
-{
-    using CH = Chains<WW, WH>;
-    if (wip == 0) {
-        const float acc = chain_sum_i4<CH::SLEN / 4>(reinterpret_cast<const int4*>(buf + (lane & 7) * CH::SLEN));
-        if (lane < 8) reinterpret_cast<float*>(buf)[CH::B_RES + lane] = acc;
-    }
-    if (wip == 1) {
-        const float acc = chain_sum_f4<CH::TLEN / 4>(reinterpret_cast<const float4*>(buf + 8 * CH::SLEN + (lane & 1) * CH::TLEN));
-        if (lane < 2) reinterpret_cast<float*>(buf)[CH::B_RES + 8 + lane] = acc;
-    }
-}
-
 // b replay, split over the point's warps: warp 0 runs the 8 SIMD chains (lane = chain; int pair -> float -> add), warp
 // TW the 2 tail chains (floats, converted by the threads that own the pixels).  Results go to buf[B_RES ..].
 template <int WW, int WH, int WPP>
@@ -385,17 +299,28 @@ __device__ __forceinline__ void replay_b(int* __restrict__ buf, int wip, int lan
     }
 }
 
-// Tracks one point through all levels (resume == nullptr) or resumes a handed-off point at (level, iteration j) of
-// *resume.  Returns false when the point exceeded the per-level iteration budget and was pushed onto the work list
-// (its outputs are then written by the team that resumes it).
-template <int WW, int WH, int WPP, bool LONG>
-__device__ __forceinline__ bool run_point(const LKLaunch& L, const long long gid0, const LKResume* __restrict__ resume,
-                                          uint8_t* ws, const int tid, const int bar)
+// ---- commands (leader -> team) ------------------------------------------------------------------------------------
+// word 0 of the mailbox: op in bits 0..7, flags in bits 8..15, pyramid level in bits 16..23
+enum : int { OP_LEVEL = 1, OP_GREPLAY = 2, OP_ITER = 3, OP_TIER1 = 4, OP_REPLAY = 5, OP_ERR = 6, OP_EXIT = 7 };
+enum : int { F_RESTAGE = 0x100, F_CLASSES = 0x200, F_JVALID = 0x400 };
+// leader state machine: what the leader does next (it consumes the partial sums of the command it issued last)
+enum : int { PH_LEVEL_START, PH_AFTER_LEVEL, PH_AFTER_GREPLAY, PH_HAVE_G, PH_ITER_NEXT, PH_AFTER_SUM3, PH_AFTER_TIER1,
+             PH_AFTER_REPLAY, PH_SOLVE, PH_LEVEL_END, PH_AFTER_ERR };
+
+// Tracks one point through all pyramid levels.  Called by all 32 * WPP threads of the team; barriers bar0 .. bar0 + 2
+// belong to the team.
+template <int WW, int WH, int WPP>
+__device__ __forceinline__ void run_point(const LKLaunch& L, const long long gid, uint8_t* ws, const int tid, const int bar0)
 {
     using C = Cfg<WW, WH, WPP>;
+    using CH = Chains<WW, WH>;
     const int lane = tid & 31;
-    const int wip = tid >> 5;                   // warp within the point
-    const long long gid = gid0;
+    const int wip = tid >> 5;                    // warp within the team
+    // (a vote makes the predicate warp-uniform for the compiler: no convergence barriers around the leader's collectives)
+    const bool leader = (WPP == 1) ? true : __all_sync(kFull, wip == 0);
+    const int barA = bar0;                       // partial sums ready: followers arrive, leader waits
+    const int barB = bar0 + 1;                   // command posted:     leader arrives, followers wait
+    const int barC = bar0 + 2;                   // full team barrier inside a command
     const int bidx = (int)(gid / L.n_per_pair);
 
     uint8_t* jreg = ws + C::OFF_J;
@@ -403,8 +328,7 @@ __device__ __forceinline__ bool run_point(const LKLaunch& L, const long long gid
     uint8_t* ireg = ws + C::OFF_I;
     int4* red3 = reinterpret_cast<int4*>(ws + C::OFF_R3);
     int* red16 = reinterpret_cast<int*>(ws + C::OFF_R16);
-    int par3 = 0, par16 = 0;
-    if (tid == 0) *reinterpret_cast<volatile long long*>(ws + C::OFF_GID) = gid;   // read back by the same thread only
+    int4* mbox = reinterpret_cast<int4*>(ws + C::OFF_CMD);
 
     // units of this thread: unit u = tid + k*NT covers window pixels (y, x0..x0+3); coordinates are recomputed where
     // needed (division by a constant), only the word offset inside the staged next-image region is kept.
@@ -414,629 +338,642 @@ __device__ __forceinline__ bool run_point(const LKLaunch& L, const long long gid
     int jw[C::UPT];
 #pragma unroll
     for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
-    // resume teams: where a unit's mismatch products go in the replay scratch (word offsets), tail unit?, last unit of a row?
-    int coff[LONG ? C::UPT : 1];
-    bool ctail[LONG ? C::UPT : 1];
-    int cnv[LONG ? C::UPT : 1];
-    if constexpr (LONG) {
-        using CH = Chains<WW, WH>;
-#pragma unroll
-        for (int k = 0; k < C::UPT; ++k) {
-            const int y = unit_y(k), x0 = unit_x0(k);
-            ctail[k] = x0 >= C::NV;
-            cnv[k] = min(4, WW - x0);
-            coff[k] = ctail[k] ? 8 * CH::SLEN + y * CH::TL + (x0 - C::NV) : (y * CH::NS + (x0 >> 3)) * 2 + ((x0 >> 2) & 1);
-        }
-    }
 
+    // ---- per-pixel state of the team (registers; valid for the current level) ----------------------------------------
+    PxStore<C::PACK> pxs[C::UPT][4];
+    DiffStore<C::PACK> dd[C::UPT];
+    int cur_level = 0;
+    bool pads_zeroed = false;
+
+    // ---- state of the leader (the followers carry these registers along unused) -----------------------------------------
     const long long t_start = clock64();
 #ifdef KLT_LK_TIMELINE
     const unsigned long long t_g0 = (L.flags & 0x400) ? gtimer() : 0ull;   // debug flag 0x400: start / end stamps (128 ns units)
-    long long ph[6] = {0, 0, 0, 0, 0, 0};   // debug flag 0x200: cycles per phase of the long-point iteration
 #endif
     int n_t1 = 0, n_t2 = 0;
-    const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
-    float2 outp = make_float2(0.f, 0.f);
-    if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) outp = reinterpret_cast<const float2*>(L.next_pts)[gid];
+    float2 p0 = make_float2(0.f, 0.f), outp = make_float2(0.f, 0.f);
+    if (leader) {
+        p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
+        if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) outp = reinterpret_cast<const float2*>(L.next_pts)[gid];
+    }
     int status = 1;
     float err = 0.f;
-    bool handed = false;
-    int iters = resume ? resume->iters : 0;
+    int iters = 0;
     const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
-    const int top = L.prev.top;
-    const int first = resume ? resume->level : top;   // a resumed point re-enters at the level it left
-    // iterations a point may spend on one level before it is handed to a resume team (0 = no hand-off)
-    // (the host leaves L.budget = 0 when no work list is attached)
+    int level = L.prev.top;
+    int phase = PH_LEVEL_START;
+    int lw = 0, lh = 0;
+    float nx = 0.f, ny = 0.f, pdx = 0.f, pdy = 0.f;
+    float A11 = 0.f, A12 = 0.f, A22 = 0.f, D = 0.f, b1 = 0.f, b2 = 0.f;
+    int jx0 = 0, jy0 = 0, jax = 0, j = 0;   // staged next-image region: smem col 0 <-> image x = jax; window columns start at jx0
+    bool jvalid = false, sticky = false;
 
-    for (int level = first; level >= 0; --level) {
-        const bool resuming = resume != nullptr && level == first;
-        const LevelView lvI = L.prev.lv[level];
-        const LevelView lvJ = L.next.lv[level];
-        const uint8_t* __restrict__ imgI = lvI.data + (long long)bidx * lvI.batch_stride;
-        const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
-        const int lw = lvI.w, lh = lvI.h;
-        const float scale = __int_as_float((127 - level) << 23);
-
-        float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
-        float nx, ny;
-        if (resuming) {
-            // position at the start of iteration resume->j, i.e. what the update of iteration j - 1 stored (j >= 1)
-            nx = __fadd_rn(resume->nx, hwx); ny = __fadd_rn(resume->ny, hwy);
-        } else if (level == top) {
-            if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(outp.x, scale); ny = __fmul_rn(outp.y, scale); }
-            else { nx = px; ny = py; }
-        } else {
-            nx = __fmul_rn(outp.x, 2.f); ny = __fmul_rn(outp.y, 2.f);
-        }
-        outp = make_float2(nx, ny);
-
-        px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
-        int ipx, ipy;
-        if (!floor_in_range(px, py, WW, WH, lw, lh, ipx, ipy)) {
-            if (level == 0) { status = 0; err = 0.f; }
-            continue;
-        }
-        int w00, w01, w10, w11;
-        q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
-
-        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
-        if (resuming) { nx = resume->nx; ny = resume->ny; }
-        // ---- stage both neighbourhoods; the previous level's readers are done (barrier below) -------------
-        point_sync<WPP>(bar);
-        int jax = 0, jy0 = 0, jx0 = 0;  // region origin: smem col 0 <-> image x = jax; window columns start at jx0
-        bool jvalid = false;
-        {
-            int inx, iny;
-            if (floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
-                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
-                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
-            }
-        }
-        const int iax = (ipx - 1) & ~3;
-        const int oi = (ipx - 1) - iax;
-        stage<C::IR, C::SI, C::NT>(ireg, lvI, imgI, iax, ipy - 1, oi, WW + 3, tid);
-        point_sync<WPP>(bar);
-
-        // ---- patch pass: Q5 intensity + Q14 derivative patch into registers, integer class sums of G ------------
-        const uint32_t W0 = (uint32_t)(w00 & 0xffff) | ((uint32_t)w01 << 16);
-        const uint32_t W1 = (uint32_t)(w10 & 0xffff) | ((uint32_t)w11 << 16);
-        PxStore<C::PACK> pxs[C::UPT][4];
-        int vals[16];
-        unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, t11 = 0, t22 = 0;
-        int q12[4] = {0, 0, 0, 0}, t12 = 0;
-        // all (WW+1) x (WH+1) derivative positions inside the image <=> no zero-masking of the derivative
-        const bool interior = (ipx >= 0) && (ipy >= 0) && (ipx + WW < lw) && (ipy + WH < lh);
-        if (interior) {
-            // Scharr is linear and so is the Q14 bilinear tap, so  sum_c w_c * Scharr(I)(p + c)  ==  Scharr(T)(p)  with
-            // T(q) = sum_c w_c * I(q + c) the UNROUNDED bilinear sum (<= 255 * 2^14); exact in int32 (|.| < 2^27).
-            const int sh = (oi & 3) * 8;
-#pragma unroll
-            for (int k = 0; k < C::UPT; ++k) {
-                const int y = unit_y(k), x0 = unit_x0(k);
-                const bool ok = unit_ok(k);
-                uint32_t pa[4], pb[4], pc[4], pd[4];   // byte pairs (c,c+1) of 4 region rows: see pair() below
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ireg + (y + r) * C::SI) + ((oi + x0) >> 2);
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-                    pa[r] = __funnelshift_r(w0, w1, sh);        // bytes c0 .. c0+3   (c0 = column of window x0-1)
-                    pb[r] = __funnelshift_rc(w0, w1, sh + 8);   // bytes c0+1 .. c0+4
-                    pc[r] = __funnelshift_r(w1, w2, sh);        // bytes c0+4 .. c0+7
-                    pd[r] = __funnelshift_rc(w1, w2, sh + 8);   // bytes c0+5 .. c0+8
-                }
-                int T[3][6];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    T[r][0] = dp2a_lo(W1, pa[r + 1], dp2a_lo(W0, pa[r], 0));
-                    T[r][1] = dp2a_lo(W1, pb[r + 1], dp2a_lo(W0, pb[r], 0));
-                    T[r][2] = dp2a_hi(W1, pa[r + 1], dp2a_hi(W0, pa[r], 0));
-                    T[r][3] = dp2a_hi(W1, pb[r + 1], dp2a_hi(W0, pb[r], 0));
-                    T[r][4] = dp2a_lo(W1, pc[r + 1], dp2a_lo(W0, pc[r], 0));
-                    T[r][5] = dp2a_lo(W1, pd[r + 1], dp2a_lo(W0, pd[r], 0));
-                }
-                int t0[6], t1[6];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    t0[c] = 3 * (T[0][c] + T[2][c]) + 10 * T[1][c];
-                    t1[c] = T[2][c] - T[0][c];
-                }
-                unsigned u11[4], u22[4];
-                int u12[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool valid = ok && (x0 + j) < WW;
-                    const int iv = (T[1][j + 1] + (1 << 8)) >> 9;
-                    int gx = (t0[j + 2] - t0[j] + (1 << 13)) >> 14;
-                    int gy = (3 * (t1[j] + t1[j + 2]) + 10 * t1[j + 1] + (1 << 13)) >> 14;
-                    gx = valid ? gx : 0; gy = valid ? gy : 0;
-                    pxs[k][j].set(valid ? iv : 0, gx, gy, max(abs(gx), abs(gy)));
-                    u11[j] = (unsigned)(gx * gx); u12[j] = gx * gy; u22[j] = (unsigned)(gy * gy);
-                }
-                const bool tail = x0 >= C::NV;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    q11[j] += tail ? 0u : u11[j];
-                    q12[j] += tail ? 0 : u12[j];
-                    q22[j] += tail ? 0u : u22[j];
-                }
-                t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
-                t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
-                t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
-            }
-        } else {
-            // border window: Scharr at the (WW+1) x (WH+1) integer positions, zero outside the image, then bilinear
-            for (int u = tid; u < C::NRUN; u += C::NT) {
-                const int dy = u / C::RPR;
-                const int dx0 = 4 * (u - dy * C::RPR);
-                const uint8_t* r0 = ireg + dy * C::SI + oi + dx0;
-                const uint8_t* r1 = r0 + C::SI;
-                const uint8_t* r2 = r1 + C::SI;
-                int t0[6], t1[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int a = r0[k], b = r1[k], cc = r2[k];
-                    t0[k] = 3 * (a + cc) + 10 * b;
-                    t1[k] = cc - a;
-                }
-                const bool yin = (unsigned)(ipy + dy) < (unsigned)lh;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int dx = dx0 + k;
-                    const int gx = t0[k + 2] - t0[k];
-                    const int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
-                    const bool in = yin && ((unsigned)(ipx + dx) < (unsigned)lw);
-                    if (dx < C::SD) dreg[dy * C::SD + dx] = in ? (((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16)) : 0u;
-                }
-            }
-            point_sync<WPP>(bar);
-#pragma unroll
-            for (int k = 0; k < C::UPT; ++k) {
-                const int y = unit_y(k), x0 = unit_x0(k);
-                const bool ok = unit_ok(k);
-                uint32_t a0, b0, a1, b1;
-                load5(ireg + (y + 1) * C::SI, oi + 1 + x0, a0, b0);
-                load5(ireg + (y + 2) * C::SI, oi + 1 + x0, a1, b1);
-                int iv[4];
-                iv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
-                iv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
-                iv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
-                iv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
-                const uint32_t* d0 = dreg + y * C::SD + x0;
-                const uint32_t* d1 = d0 + C::SD;
-                const uint4 e0 = *reinterpret_cast<const uint4*>(d0);
-                const uint4 e1 = *reinterpret_cast<const uint4*>(d1);
-                const uint32_t r0w[5] = {e0.x, e0.y, e0.z, e0.w, d0[4]};
-                const uint32_t r1w[5] = {e1.x, e1.y, e1.z, e1.w, d1[4]};
-                unsigned u11[4], u22[4];
-                int u12[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int gx = (lo16(r0w[j]) * w00 + lo16(r0w[j + 1]) * w01 + lo16(r1w[j]) * w10 + lo16(r1w[j + 1]) * w11 + (1 << 13)) >> 14;
-                    int gy = (hi16(r0w[j]) * w00 + hi16(r0w[j + 1]) * w01 + hi16(r1w[j]) * w10 + hi16(r1w[j + 1]) * w11 + (1 << 13)) >> 14;
-                    const bool valid = ok && (x0 + j) < WW;
-                    gx = valid ? gx : 0; gy = valid ? gy : 0;
-                    pxs[k][j].set(valid ? iv[j] : 0, gx, gy, max(abs(gx), abs(gy)));
-                    u11[j] = (unsigned)(gx * gx); u12[j] = gx * gy; u22[j] = (unsigned)(gy * gy);
-                }
-                const bool tail = x0 >= C::NV;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    q11[j] += tail ? 0u : u11[j];
-                    q12[j] += tail ? 0 : u12[j];
-                    q22[j] += tail ? 0u : u22[j];
-                }
-                t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
-                t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
-                t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
-            }
-        }
-        {
-            const unsigned cap = (1u << 25) / WPP;  // keeps the point-wide totals below 2^31
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                vals[j] = (int)min(q11[j], cap);
-                vals[5 + j] = max(min(q12[j], (int)cap), -(int)cap);
-                vals[10 + j] = (int)min(q22[j], cap);
-            }
-            vals[4] = (int)min(t11, cap);
-            vals[9] = max(min(t12, (int)cap), -(int)cap);
-            vals[14] = (int)min(t22, cap);
-            vals[15] = 0;
-        }
-        // lane L < 15 now holds class total L: [0..4] = gx*gx (4 SIMD lanes, tail), [5..9] = gx*gy, [10..14] = gy*gy
-        const int gtot = point_sum15_lane<WPP>(vals, red16, par16, wip, lane, bar);
-
-        float A11, A12, A22;
-        {
-            // A11 / A22: non-negative terms, exact iff every class total <= 2^24; A12: |gx gy| <= (gx^2 + gy^2) / 2
-            const unsigned partner = (unsigned)__shfl_sync(kFull, gtot, (lane + 10) & 31);
-            const bool ok = (lane >= 5) || ((unsigned)gtot <= (unsigned)kExact && partner <= (unsigned)kExact &&
-                                            (unsigned)gtot + partner <= 2u * (unsigned)kExact);
-            if (__all_sync(kFull, ok)) {
-                const float f = (float)gtot;
-                A11 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
-                               __shfl_sync(kFull, f, 4));
-                A12 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
-                               __shfl_sync(kFull, f, 9));
-                A22 = combine5(__shfl_sync(kFull, f, 10), __shfl_sync(kFull, f, 11), __shfl_sync(kFull, f, 12), __shfl_sync(kFull, f, 13),
-                               __shfl_sync(kFull, f, 14));
-            } else {
-                // serial replay in OpenCV's order (A.5): every thread stores the float products of its pixels in chain
-                // order; all scratch is dead here (every warp passed the exchange barrier above)
-                using CH = Chains<WW, WH>;
-                float* gf = reinterpret_cast<float*>(dreg);
-#pragma unroll
-                for (int k = 0; k < C::UPT; ++k)
-                    if (unit_ok(k)) {
-                        const int y = unit_y(k), x0 = unit_x0(k);
-                        const bool tail = x0 >= C::NV;
-                        float* g0 = tail ? gf + 12 * CH::GQ4 + y * CH::TL + (x0 - C::NV) : gf + y * (C::NV / 4) + (x0 >> 2);
-                        const int sj = tail ? 1 : CH::GQ4;            // next pixel: next element of the tail / next lane chain
-                        const int ss = tail ? CH::GT4 : 4 * CH::GQ4;  // next sum
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (x0 + j < WW) {
-                                const int gx = pxs[k][j].gx(), gy = pxs[k][j].gy();
-                                g0[j * sj] = (float)(gx * gx);
-                                g0[j * sj + ss] = (float)(gx * gy);
-                                g0[j * sj + 2 * ss] = (float)(gy * gy);
-                            }
+    for (;;) {
+        int c_op = 0, c_a = 0, c_b = 0, c_jx0 = 0, c_jy0 = 0;
+        uint32_t c_W0 = 0, c_W1 = 0;
+        if (leader) {
+            // ================= leader step: consume the partial sums of the last command, advance to the next command ===
+            bool produced = false;
+#pragma unroll 1
+            while (!produced) {
+                switch (phase) {
+                case PH_LEVEL_START: {
+                    if (level < 0) { c_op = OP_EXIT; produced = true; break; }
+                    lw = L.prev.lv[level].w; lh = L.prev.lv[level].h;
+                    const float scale = __int_as_float((127 - level) << 23);
+                    float px = __fmul_rn(p0.x, scale), py = __fmul_rn(p0.y, scale);
+                    if (level == L.prev.top) {
+                        if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(outp.x, scale); ny = __fmul_rn(outp.y, scale); }
+                        else { nx = px; ny = py; }
+                    } else {
+                        nx = __fmul_rn(outp.x, 2.f); ny = __fmul_rn(outp.y, 2.f);
                     }
-                {   // zero pads
-                    constexpr int PQ = CH::GQ4 - CH::GQ, PT = CH::GT4 - CH::GT;
-                    if (tid < 12 * PQ) gf[(tid / (PQ > 0 ? PQ : 1)) * CH::GQ4 + CH::GQ + tid % (PQ > 0 ? PQ : 1)] = 0.f;
-                    if (tid < 3 * PT) gf[12 * CH::GQ4 + (tid / (PT > 0 ? PT : 1)) * CH::GT4 + CH::GT + tid % (PT > 0 ? PT : 1)] = 0.f;
+                    outp = make_float2(nx, ny);
+                    px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+                    int ipx, ipy;
+                    if (!floor_in_range(px, py, WW, WH, lw, lh, ipx, ipy)) {
+                        if (level == 0) { status = 0; err = 0.f; }
+                        --level;
+                        break;
+                    }
+                    int w00, w01, w10, w11;
+                    q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+                    nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+                    int inx, iny;
+                    jvalid = floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny);
+                    if (jvalid) { jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; }
+                    c_op = OP_LEVEL | (level << 16) | (jvalid ? F_JVALID : 0);
+                    c_a = ipx; c_b = ipy;
+                    c_W0 = (uint32_t)(w00 & 0xffff) | ((uint32_t)w01 << 16);
+                    c_W1 = (uint32_t)(w10 & 0xffff) | ((uint32_t)w11 << 16);
+                    c_jx0 = jx0; c_jy0 = jy0;
+                    phase = PH_AFTER_LEVEL; produced = true;
+                    break;
                 }
-                point_sync<WPP>(bar);
-                replay_g<WW, WH, WPP>(gf, wip, lane);
-                point_sync<WPP>(bar);
-                const float* r = gf + CH::G_RES;
-                A11 = combine5(r[0], r[1], r[2], r[3], r[4]);
-                A12 = combine5(r[5], r[6], r[7], r[8], r[9]);
-                A22 = combine5(r[10], r[11], r[12], r[13], r[14]);
-            }
-        }
-        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-        const float dA = __fsub_rn(A11, A22);
-        const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)));
-        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), rad), (float)(2 * WW * WH));
-        if (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) err = min_eig;
-        if (min_eig < L.min_eig_thr || D < 1.1920929e-7f) {
-            if (level == 0) status = 0;
-            continue;
-        }
-        D = __fdiv_rn(1.f, D);
-
-        // ---- iterations ------------------------------------------------------------------------------------
-        // make sure the staged next-image region covers the window at (inx, iny)
-        auto ensure_j = [&](int inx, int iny) {
-            if (!jvalid || inx < jx0 || iny < jy0 || inx + WW + 1 > jx0 + C::JW || iny + WH + 1 > jy0 + C::JR) {
-                point_sync<WPP>(bar);
-                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
-                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
-                point_sync<WPP>(bar);
-            }
-        };
-
-        float pdx = resuming ? resume->pdx : 0.f, pdy = resuming ? resume->pdy : 0.f;
-        bool sticky = resuming, pads_zeroed = false;
-        for (int j = resuming ? resume->j : 0; j < L.max_count; ++j) {
-            if (!LONG && j == L.budget && L.budget > 0) {
-                // Long point (99.4 % of the (point, level) pairs of a KITTI frame converge within 6 iterations): it would
-                // bound the launch while occupying a slot of the bulk shape, so it continues on a resume team.
-                if (tid == 0) {
-                    const int slot = atomicAdd(L.wl_ctrl, 1);
-                    push_entry(L, slot, *reinterpret_cast<volatile long long*>(ws + C::OFF_GID), level, j, nx, ny, pdx, pdy, iters);
+                case PH_AFTER_LEVEL: {
+                    // lane L < 15 holds class total L: [0..4] = gx*gx (4 SIMD lanes, tail), [5..9] = gx*gy, [10..14] = gy*gy
+                    const int4 t = reinterpret_cast<const int4*>(red16)[lane & 15];
+                    const int gtot = t.x + (WPP > 1 ? t.y : 0) + (WPP > 2 ? t.z + t.w : 0);
+                    // A11 / A22: non-negative terms, exact iff every class total <= 2^24; A12: |gx gy| <= (gx^2 + gy^2) / 2
+                    const unsigned partner = (unsigned)__shfl_sync(kFull, gtot, (lane + 10) & 31);
+                    const bool ok = (lane >= 5) || ((unsigned)gtot <= (unsigned)kExact && partner <= (unsigned)kExact &&
+                                                    (unsigned)gtot + partner <= 2u * (unsigned)kExact);
+                    if (__all_sync(kFull, ok)) {
+                        const float f = (float)gtot;
+                        A11 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
+                                       __shfl_sync(kFull, f, 4));
+                        A12 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
+                                       __shfl_sync(kFull, f, 9));
+                        A22 = combine5(__shfl_sync(kFull, f, 10), __shfl_sync(kFull, f, 11), __shfl_sync(kFull, f, 12), __shfl_sync(kFull, f, 13),
+                                       __shfl_sync(kFull, f, 14));
+                        phase = PH_HAVE_G;
+                    } else {
+                        c_op = OP_GREPLAY; phase = PH_AFTER_GREPLAY; produced = true;
+                    }
+                    break;
                 }
-                handed = true;
-                break;
+                case PH_AFTER_GREPLAY: {
+                    const float* r = reinterpret_cast<const float*>(dreg) + CH::G_RES;
+                    A11 = combine5(r[0], r[1], r[2], r[3], r[4]);
+                    A12 = combine5(r[5], r[6], r[7], r[8], r[9]);
+                    A22 = combine5(r[10], r[11], r[12], r[13], r[14]);
+                    phase = PH_HAVE_G;
+                    break;
+                }
+                case PH_HAVE_G: {
+                    D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+                    const float dA = __fsub_rn(A11, A22);
+                    const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)));
+                    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), rad), (float)(2 * WW * WH));
+                    if (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) err = min_eig;
+                    if (min_eig < L.min_eig_thr || D < 1.1920929e-7f) {
+                        if (level == 0) status = 0;
+                        --level; phase = PH_LEVEL_START;
+                        break;
+                    }
+                    D = __fdiv_rn(1.f, D);
+                    j = 0; pdx = 0.f; pdy = 0.f; sticky = false;
+                    phase = PH_ITER_NEXT;
+                    break;
+                }
+                case PH_ITER_NEXT: {
+                    if (j >= L.max_count) { phase = PH_LEVEL_END; break; }
+                    int inx, iny;
+                    if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
+                        if (level == 0) status = 0;
+                        phase = PH_LEVEL_END;
+                        break;
+                    }
+                    ++iters;
+                    // make sure the staged next-image region covers the window at (inx, iny)
+                    const bool restage = !jvalid || (unsigned)(inx - jx0) > (unsigned)(2 * kM) || (unsigned)(iny - jy0) > (unsigned)(2 * kM);
+                    if (restage) { jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true; }
+                    int v00, v01, v10, v11;
+                    q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
+                    c_W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
+                    c_W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
+                    c_a = (iny - jy0) * C::SJ + (inx - jax);
+                    c_jx0 = jx0; c_jy0 = jy0;
+                    // Tier 0 (whole-window bounds) unless the previous iteration of this point already failed it ("sticky"):
+                    // diverging points fail it every time, and they are the ones that bound the launch latency.
+                    c_op = OP_ITER | (restage ? F_RESTAGE : 0) | (sticky ? F_CLASSES : 0);
+                    if (sticky) ++n_t1;
+                    phase = sticky ? PH_AFTER_TIER1 : PH_AFTER_SUM3;
+                    produced = true;
+                    break;
+                }
+                case PH_AFTER_SUM3: {
+                    int s1 = 0, s2 = 0;
+                    unsigned bx = 0, by = 0;
+#pragma unroll
+                    for (int w = 0; w < WPP; ++w) {
+                        const int4 v = red3[w];
+                        s1 += v.x; s2 += v.y; bx += (unsigned)v.z; by += (unsigned)v.w;
+                    }
+                    if (bx <= (unsigned)kExact && by <= (unsigned)kExact) {
+                        // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
+                        b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
+                        b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
+                        phase = PH_SOLVE;
+                    } else {
+                        sticky = true; ++n_t1;
+                        c_op = OP_TIER1; phase = PH_AFTER_TIER1; produced = true;
+                    }
+                    break;
+                }
+                case PH_AFTER_TIER1: {
+                    // tier 1: per accumulation class (4 SIMD lanes + tail), bound in units of 16 (rounded up per pixel)
+                    const int4 t = reinterpret_cast<const int4*>(red16)[lane & 15];
+                    const int ctot = t.x + (WPP > 1 ? t.y : 0) + (WPP > 2 ? t.z + t.w : 0);
+                    const bool is_bound = (lane >= 10) && (lane < 15);
+                    const bool exact = __all_sync(kFull, !is_bound || ctot <= (kExact >> 4));
+                    // leave sticky mode once the whole-window bound would pass again (converging point)
+                    sticky = __reduce_add_sync(kFull, is_bound ? ctot : 0) > (kExact >> 4);
+                    if (exact) {
+                        const float f = (float)ctot;
+                        b1 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
+                                      __shfl_sync(kFull, f, 4));
+                        b2 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
+                                      __shfl_sync(kFull, f, 9));
+                        phase = PH_SOLVE;
+                    } else {
+                        ++n_t2;
+                        c_op = OP_REPLAY; phase = PH_AFTER_REPLAY; produced = true;
+                    }
+                    break;
+                }
+                case PH_AFTER_REPLAY: {
+                    const int* buf = reinterpret_cast<const int*>(dreg);
+                    const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
+                    const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
+                    const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
+                    b1 = combine5(r1.x, r1.y, r1.z, r1.w, rt.x);
+                    b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
+                    phase = PH_SOLVE;
+                    break;
+                }
+                case PH_SOLVE: {
+                    const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+                    const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+                    nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+                    outp = make_float2(__fadd_rn(nx, hwx), __fadd_rn(ny, hwy));
+                    phase = PH_ITER_NEXT;
+                    {   // termination tests of A.4 6f / 6g without double-precision instructions on the common path
+                        const float s2f = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                        bool small = s2f <= L.eps2_lo;
+                        if (!small && !(s2f >= L.eps2_hi))
+                            small = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2;
+                        if (small) { phase = PH_LEVEL_END; break; }
+                    }
+                    // (double)f < 0.01  <=>  f <= 0.01f: the float nearest to 0.01 lies below it, the next float above it
+                    if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
+                        outp.x = __fsub_rn(outp.x, __fmul_rn(dx, 0.5f));
+                        outp.y = __fsub_rn(outp.y, __fmul_rn(dy, 0.5f));
+                        phase = PH_LEVEL_END;
+                        break;
+                    }
+                    pdx = dx; pdy = dy; ++j;
+                    break;
+                }
+                case PH_LEVEL_END: {
+                    // ---- err at level 0 -------------------------------------------------------------------------------
+                    if (status && level == 0 && (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) == 0) {
+                        const float qx = __fsub_rn(outp.x, hwx), qy = __fsub_rn(outp.y, hwy);
+                        int iqx, iqy;
+                        if (!floor_in_range(qx, qy, WW, WH, lw, lh, iqx, iqy)) {
+                            status = 0;
+                            --level; phase = PH_LEVEL_START;
+                            break;
+                        }
+                        const bool restage = !jvalid || (unsigned)(iqx - jx0) > (unsigned)(2 * kM) || (unsigned)(iqy - jy0) > (unsigned)(2 * kM);
+                        if (restage) { jx0 = iqx - kM; jy0 = iqy - kM; jax = jx0 & ~3; jvalid = true; }
+                        int v00, v01, v10, v11;
+                        q14_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), v00, v01, v10, v11);
+                        c_W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
+                        c_W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
+                        c_a = (iqy - jy0) * C::SJ + (iqx - jax);
+                        c_jx0 = jx0; c_jy0 = jy0;
+                        c_op = OP_ERR | (restage ? F_RESTAGE : 0);
+                        phase = PH_AFTER_ERR; produced = true;
+                    } else {
+                        --level; phase = PH_LEVEL_START;
+                    }
+                    break;
+                }
+                default: {   // PH_AFTER_ERR
+                    int e = 0;
+#pragma unroll
+                    for (int w = 0; w < WPP; ++w) e += red3[w].x;
+                    // |d| <= 8160 and WW*WH <= 2056 for the instantiated windows: e <= 2^24, so OpenCV's float32 running sum is exact
+                    err = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * WW * WH));
+                    --level; phase = PH_LEVEL_START;
+                    break;
+                }
+                }
             }
-            int inx, iny;
-            if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
-                if (level == 0) status = 0;
-                break;
+            if constexpr (WPP > 1) {
+                if (lane == 0) {
+                    mbox[0] = make_int4(c_op, c_a, (int)c_W0, (int)c_W1);
+                    mbox[1] = make_int4(c_jx0, c_jy0, c_b, 0);
+                }
+                team_arrive<WPP>(barB);
             }
-            ++iters;
-#ifdef KLT_LK_TIMELINE
-            long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;
-            if constexpr (LONG) tq0 = clock64();
-#define KLT_TQ(v) v = clock64()
-#else
-#define KLT_TQ(v)
-#endif
-            ensure_j(inx, iny);
-            int v00, v01, v10, v11;
-            q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
-            const uint32_t W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
-            const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
-            float b1 = 0.f, b2 = 0.f;
-            if constexpr (LONG) {
-                // Resume teams: the points they serve failed the exactness bounds on nearly every iteration of the bulk
-                // shape, so the mismatch products go straight into OpenCV's accumulation chains (always exact).
-                using CH = Chains<WW, WH>;
-                int* buf = reinterpret_cast<int*>(dreg);
-                if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }
-                const int cb = (iny - jy0) * C::SJ + (inx - jax);
-                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
-                const int sh = (cb & 3) * 8;
-                ++n_t2;
-                KLT_TQ(tq1);
+        } else {
+            team_sync<WPP>(barB);
+            const int4 m0 = mbox[0];
+            const int4 m1 = mbox[1];
+            c_op = m0.x; c_a = m0.y; c_W0 = (uint32_t)m0.z; c_W1 = (uint32_t)m0.w;
+            c_jx0 = m1.x; c_jy0 = m1.y; c_b = m1.z;
+        }
+
+        // ================= the team executes the command ==================================================================
+        const int op = c_op & 0xff;
+        if (op == OP_EXIT) break;
+        if (op == OP_LEVEL) {
+            cur_level = (c_op >> 16) & 0xff;
+            pads_zeroed = false;
+            const LevelView lvI = L.prev.lv[cur_level];
+            const LevelView lvJ = L.next.lv[cur_level];
+            const uint8_t* __restrict__ imgI = lvI.data + (long long)bidx * lvI.batch_stride;
+            const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
+            const int tlw = lvI.w, tlh = lvI.h;
+            const int ipx = c_a, ipy = c_b;
+            const uint32_t W0 = c_W0, W1 = c_W1;
+            // ---- stage both neighbourhoods (everybody has finished the previous command) --------------------------------
+            if (c_op & F_JVALID) {
+                const int sax = c_jx0 & ~3;
+                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, sax, c_jy0, c_jx0 - sax, C::JW, tid);
+            }
+            const int iax = (ipx - 1) & ~3;
+            const int oi = (ipx - 1) - iax;
+            stage<C::IR, C::SI, C::NT>(ireg, lvI, imgI, iax, ipy - 1, oi, WW + 3, tid);
+            team_sync<WPP>(barC);
+
+            // ---- patch pass: Q5 intensity + Q14 derivative patch into registers, integer class sums of G ------------
+            int vals[16];
+            unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, t11 = 0, t22 = 0;
+            int q12[4] = {0, 0, 0, 0}, t12 = 0;
+            // all (WW+1) x (WH+1) derivative positions inside the image <=> no zero-masking of the derivative
+            const bool interior = (ipx >= 0) && (ipy >= 0) && (ipx + WW < tlw) && (ipy + WH < tlh);
+            if (interior) {
+                // Scharr is linear and so is the Q14 bilinear tap, so  sum_c w_c * Scharr(I)(p + c)  ==  Scharr(T)(p)  with
+                // T(q) = sum_c w_c * I(q + c) the UNROUNDED bilinear sum (<= 255 * 2^14); exact in int32 (|.| < 2^27).
+                const int sh = (oi & 3) * 8;
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const int y = unit_y(k), x0 = unit_x0(k);
+                    const bool ok = unit_ok(k);
+                    uint32_t pa[4], pb[4], pc[4], pd[4];   // byte pairs (c,c+1) of 4 region rows
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(ireg + (y + r) * C::SI) + ((oi + x0) >> 2);
+                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                        pa[r] = __funnelshift_r(w0, w1, sh);        // bytes c0 .. c0+3   (c0 = column of window x0-1)
+                        pb[r] = __funnelshift_rc(w0, w1, sh + 8);   // bytes c0+1 .. c0+4
+                        pc[r] = __funnelshift_r(w1, w2, sh);        // bytes c0+4 .. c0+7
+                        pd[r] = __funnelshift_rc(w1, w2, sh + 8);   // bytes c0+5 .. c0+8
+                    }
+                    int T[3][6];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        T[r][0] = dp2a_lo(W1, pa[r + 1], dp2a_lo(W0, pa[r], 0));
+                        T[r][1] = dp2a_lo(W1, pb[r + 1], dp2a_lo(W0, pb[r], 0));
+                        T[r][2] = dp2a_hi(W1, pa[r + 1], dp2a_hi(W0, pa[r], 0));
+                        T[r][3] = dp2a_hi(W1, pb[r + 1], dp2a_hi(W0, pb[r], 0));
+                        T[r][4] = dp2a_lo(W1, pc[r + 1], dp2a_lo(W0, pc[r], 0));
+                        T[r][5] = dp2a_lo(W1, pd[r + 1], dp2a_lo(W0, pd[r], 0));
+                    }
+                    int t0[6], t1[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        t0[c] = 3 * (T[0][c] + T[2][c]) + 10 * T[1][c];
+                        t1[c] = T[2][c] - T[0][c];
+                    }
+                    unsigned u11[4], u22[4];
+                    int u12[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const bool valid = ok && (x0 + jj) < WW;
+                        const int iv = (T[1][jj + 1] + (1 << 8)) >> 9;
+                        int gx = (t0[jj + 2] - t0[jj] + (1 << 13)) >> 14;
+                        int gy = (3 * (t1[jj] + t1[jj + 2]) + 10 * t1[jj + 1] + (1 << 13)) >> 14;
+                        gx = valid ? gx : 0; gy = valid ? gy : 0;
+                        pxs[k][jj].set(valid ? iv : 0, gx, gy);
+                        u11[jj] = (unsigned)(gx * gx); u12[jj] = gx * gy; u22[jj] = (unsigned)(gy * gy);
+                    }
+                    const bool tail = x0 >= C::NV;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        q11[jj] += tail ? 0u : u11[jj];
+                        q12[jj] += tail ? 0 : u12[jj];
+                        q22[jj] += tail ? 0u : u22[jj];
+                    }
+                    t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
+                    t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
+                    t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
+                }
+            } else {
+                // border window: Scharr at the (WW+1) x (WH+1) integer positions, zero outside the image, then bilinear
+                const int w00 = lo16(W0), w01 = hi16(W0), w10 = lo16(W1), w11 = hi16(W1);
+                for (int u = tid; u < C::NRUN; u += C::NT) {
+                    const int dy = u / C::RPR;
+                    const int dx0 = 4 * (u - dy * C::RPR);
+                    const uint8_t* r0 = ireg + dy * C::SI + oi + dx0;
+                    const uint8_t* r1 = r0 + C::SI;
+                    const uint8_t* r2 = r1 + C::SI;
+                    int t0[6], t1[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int a = r0[k], b = r1[k], cc = r2[k];
+                        t0[k] = 3 * (a + cc) + 10 * b;
+                        t1[k] = cc - a;
+                    }
+                    const bool yin = (unsigned)(ipy + dy) < (unsigned)tlh;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int dx = dx0 + k;
+                        const int gx = t0[k + 2] - t0[k];
+                        const int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
+                        const bool in = yin && ((unsigned)(ipx + dx) < (unsigned)tlw);
+                        if (dx < C::SD) dreg[dy * C::SD + dx] = in ? (((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16)) : 0u;
+                    }
+                }
+                team_sync<WPP>(barC);
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const int y = unit_y(k), x0 = unit_x0(k);
+                    const bool ok = unit_ok(k);
+                    uint32_t a0, b0, a1, b1_;
+                    load5(ireg + (y + 1) * C::SI, oi + 1 + x0, a0, b0);
+                    load5(ireg + (y + 2) * C::SI, oi + 1 + x0, a1, b1_);
+                    int iv[4];
+                    iv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                    iv[1] = dp2a_lo(W1, b1_, dp2a_lo(W0, b0, 256)) >> 9;
+                    iv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                    iv[3] = dp2a_hi(W1, b1_, dp2a_hi(W0, b0, 256)) >> 9;
+                    const uint32_t* d0 = dreg + y * C::SD + x0;
+                    const uint32_t* d1 = d0 + C::SD;
+                    const uint4 e0 = *reinterpret_cast<const uint4*>(d0);
+                    const uint4 e1 = *reinterpret_cast<const uint4*>(d1);
+                    const uint32_t r0w[5] = {e0.x, e0.y, e0.z, e0.w, d0[4]};
+                    const uint32_t r1w[5] = {e1.x, e1.y, e1.z, e1.w, d1[4]};
+                    unsigned u11[4], u22[4];
+                    int u12[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        int gx = (lo16(r0w[jj]) * w00 + lo16(r0w[jj + 1]) * w01 + lo16(r1w[jj]) * w10 + lo16(r1w[jj + 1]) * w11 + (1 << 13)) >> 14;
+                        int gy = (hi16(r0w[jj]) * w00 + hi16(r0w[jj + 1]) * w01 + hi16(r1w[jj]) * w10 + hi16(r1w[jj + 1]) * w11 + (1 << 13)) >> 14;
+                        const bool valid = ok && (x0 + jj) < WW;
+                        gx = valid ? gx : 0; gy = valid ? gy : 0;
+                        pxs[k][jj].set(valid ? iv[jj] : 0, gx, gy);
+                        u11[jj] = (unsigned)(gx * gx); u12[jj] = gx * gy; u22[jj] = (unsigned)(gy * gy);
+                    }
+                    const bool tail = x0 >= C::NV;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        q11[jj] += tail ? 0u : u11[jj];
+                        q12[jj] += tail ? 0 : u12[jj];
+                        q22[jj] += tail ? 0u : u22[jj];
+                    }
+                    t11 += tail ? (u11[0] + u11[1] + u11[2] + u11[3]) : 0u;
+                    t12 += tail ? (u12[0] + u12[1] + u12[2] + u12[3]) : 0;
+                    t22 += tail ? (u22[0] + u22[1] + u22[2] + u22[3]) : 0u;
+                }
+                // the replay scratch aliases dreg: the Scharr words are dead once every thread has passed the exchange below
+            }
+            {
+                const unsigned cap = (1u << 25) / WPP;  // keeps the point-wide totals below 2^31
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    vals[jj] = (int)min(q11[jj], cap);
+                    vals[5 + jj] = max(min(q12[jj], (int)cap), -(int)cap);
+                    vals[10 + jj] = (int)min(q22[jj], cap);
+                }
+                vals[4] = (int)min(t11, cap);
+                vals[9] = max(min(t12, (int)cap), -(int)cap);
+                vals[14] = (int)min(t22, cap);
+                vals[15] = 0;
+            }
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 15; ++i) {
+                const int t = __reduce_add_sync(kFull, vals[i]);
+                mine = (lane == i) ? t : mine;
+            }
+            if (lane < 15) red16[lane * 4 + wip] = mine;
+        } else if (op == OP_ITER || op == OP_ERR) {
+            if (c_op & F_RESTAGE) {
+                // (everybody has finished reading the old region: the previous command is complete)
+                const LevelView lvJ = L.next.lv[cur_level];
+                const uint8_t* __restrict__ imgJ = lvJ.data + (long long)bidx * lvJ.batch_stride;
+                const int sax = c_jx0 & ~3;
+                stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, sax, c_jy0, c_jx0 - sax, C::JW, tid);
+                team_sync<WPP>(barC);
+            }
+            const uint32_t W0 = c_W0, W1 = c_W1;
+            const int cb = c_a;
+            const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
+            const int sh = (cb & 3) * 8;
+            if (op == OP_ERR) {
+                int e = 0;
 #pragma unroll
                 for (int k = 0; k < C::UPT; ++k) {
                     const uint32_t* __restrict__ r0 = jbase + jw[k];
                     const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
-                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
-                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
+                    const uint32_t p0_ = r0[0], p1_ = r0[1], q0 = r1[0], q1 = r1[1];
+                    const uint32_t a0 = __funnelshift_r(p0_, p1_, sh), b0 = __funnelshift_rc(p0_, p1_, sh + 8);
                     const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1_ = __funnelshift_rc(q0, q1, sh + 8);
                     int jv[4];
                     jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
                     jv[1] = dp2a_lo(W1, b1_, dp2a_lo(W0, b0, 256)) >> 9;
                     jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
                     jv[3] = dp2a_hi(W1, b1_, dp2a_hi(W0, b0, 256)) >> 9;
-                    if (unit_ok(k)) {
-                        if (ctail[k]) {
-                            float* tf = reinterpret_cast<float*>(buf) + coff[k];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                if (jj < cnv[k]) {
-                                    const int d = jv[jj] - pxs[k][jj].iv();
-                                    tf[jj] = (float)(d * pxs[k][jj].gx());
-                                    tf[CH::TLEN + jj] = (float)(d * pxs[k][jj].gy());
-                                }
-                        } else {
-                            int* si = buf + coff[k];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int d = jv[jj] - pxs[k][jj].iv();
-                                si[jj * CH::SLEN] = d * pxs[k][jj].gx();
-                                si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
-                            }
-                        }
-                    }
-                }
-                KLT_TQ(tq2);
-                point_sync<WPP>(bar);
-                KLT_TQ(tq3);
-                replay_b_long<WW, WH>(buf, wip, lane);
-                KLT_TQ(tq4);
-                point_sync<WPP>(bar);
-                KLT_TQ(tq5);
-                const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
-                const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
-                const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
-                b1 = combine5(r1.x, r1.y, r1.z, r1.w, rt.x);
-                b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
-            } else {
-            DiffStore<C::PACK> dd[C::UPT];
-            int s1, s2, bnd;
-            {
-                // invalid pixels carry gx = gy = gm = 0, so they drop out of all three sums without a select
-                const int cb = (iny - jy0) * C::SJ + (inx - jax);
-                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
-                const int sh = (cb & 3) * 8;
-                s1 = 0; s2 = 0; bnd = 0;
-#pragma unroll
-                for (int k = 0; k < C::UPT; ++k) {
-                    const uint32_t* __restrict__ r0 = jbase + jw[k];
-                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
-                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
-                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
-                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_rc(q0, q1, sh + 8);
-                    int jv[4];
-                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
-                    jv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
-                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
-                    jv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int d = jv[jj] - pxs[k][jj].iv();
-                        dd[k].set(jj, d);
-                        s1 += d * pxs[k][jj].gx();
-                        s2 += d * pxs[k][jj].gy();
-                        bnd += abs(d) * pxs[k][jj].gm();
-                    }
-                }
-            }
-            // Tier 0 (whole-window bound) unless the previous iteration of this point already failed it ("sticky"):
-            // diverging points fail it every time, and they are the ones that bound the launch latency.
-            bool classes = sticky;
-            if (!sticky) {
-                // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamp so the point total cannot wrap
-                bnd = min(bnd, (1 << 25) / WPP);
-                point_sum3<WPP>(s1, s2, bnd, red3, par3, wip, lane, bar);
-                if (bnd <= kExact) {
-                    // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
-                    b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
-                    b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
-                } else {
-                    sticky = true;
-                    classes = true;
-                }
-            }
-            if (classes) {
-                // tier 1: per accumulation class (4 SIMD lanes + tail), bound in units of 16 (rounded up per pixel)
-                ++n_t1;
-                int cv[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) cv[i] = 0;
-#pragma unroll
-                for (int k = 0; k < C::UPT; ++k) {
-                    int u1[4], u2[4], ub[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int d = dd[k].get(jj);
-                        u1[jj] = d * pxs[k][jj].gx();
-                        u2[jj] = d * pxs[k][jj].gy();
-                        ub[jj] = (abs(d) * pxs[k][jj].gm() + 15) >> 4;
-                    }
-                    const bool tail = unit_x0(k) >= C::NV;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        cv[jj] += tail ? 0 : u1[jj];
-                        cv[5 + jj] += tail ? 0 : u2[jj];
-                        cv[10 + jj] += tail ? 0 : ub[jj];
-                    }
-                    cv[4] += tail ? (u1[0] + u1[1] + u1[2] + u1[3]) : 0;
-                    cv[9] += tail ? (u2[0] + u2[1] + u2[2] + u2[3]) : 0;
-                    cv[14] += tail ? (ub[0] + ub[1] + ub[2] + ub[3]) : 0;
-                }
-#pragma unroll
-                for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (1 << 22) / WPP);
-                const int ctot = point_sum15_lane<WPP>(cv, red16, par16, wip, lane, bar);
-                const bool is_bound = (lane >= 10) && (lane < 15);
-                const bool exact = __all_sync(kFull, !is_bound || ctot <= (kExact >> 4));
-                // leave sticky mode once the whole-window bound would pass again (converging point)
-                sticky = __reduce_add_sync(kFull, is_bound ? ctot : 0) > (kExact >> 4);
-                if (exact) {
-                    const float f = (float)ctot;
-                    b1 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
-                                  __shfl_sync(kFull, f, 4));
-                    b2 = combine5(__shfl_sync(kFull, f, 5), __shfl_sync(kFull, f, 6), __shfl_sync(kFull, f, 7), __shfl_sync(kFull, f, 8),
-                                  __shfl_sync(kFull, f, 9));
-                } else {
-                    // tier 2: serial replay (pairs (l, l+4) summed in int32 first; A.5).  The scratch is rewritten by the
-                    // next replay only after every warp has passed that replay's first barrier, i.e. after it has read
-                    // these results.
-                    ++n_t2;
-                    using CH = Chains<WW, WH>;
-                    int* buf = reinterpret_cast<int*>(dreg);
-                    if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }  // pads survive until the next level
-#pragma unroll
-                    for (int k = 0; k < C::UPT; ++k)
-                        if (unit_ok(k)) {
-                            const int y = unit_y(k), x0 = unit_x0(k);
-                            if (x0 >= C::NV) {
-                                float* tf = reinterpret_cast<float*>(buf) + 8 * CH::SLEN + y * CH::TL + (x0 - C::NV);
-#pragma unroll
-                                for (int jj = 0; jj < 4; ++jj)
-                                    if (x0 + jj < WW) {
-                                        const int d = dd[k].get(jj);
-                                        tf[jj] = (float)(d * pxs[k][jj].gx());
-                                        tf[CH::TLEN + jj] = (float)(d * pxs[k][jj].gy());
-                                    }
-                            } else {
-                                int* si = buf + (y * CH::NS + (x0 >> 3)) * 2 + ((x0 >> 2) & 1);
-#pragma unroll
-                                for (int jj = 0; jj < 4; ++jj) {
-                                    const int d = dd[k].get(jj);
-                                    si[jj * CH::SLEN] = d * pxs[k][jj].gx();
-                                    si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
-                                }
-                            }
-                        }
-                    point_sync<WPP>(bar);
-                    replay_b<WW, WH, WPP>(buf, wip, lane);
-                    point_sync<WPP>(bar);
-                    const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
-                    const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
-                    const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
-                    b1 = combine5(r1.x, r1.y, r1.z, r1.w, rt.x);
-                    b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
-                }
-            }
-            }   // !LONG
-            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
-            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
-            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
-            outp = make_float2(__fadd_rn(nx, hwx), __fadd_rn(ny, hwy));
-            {   // termination tests of A.4 6f / 6g without double-precision instructions on the common path
-                const float s2f = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                bool small = s2f <= L.eps2_lo;
-                if (!small && !(s2f >= L.eps2_hi))
-                    small = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= L.eps2;
-                if (small) break;
-            }
-            // (double)f < 0.01  <=>  f <= 0.01f: the float nearest to 0.01 lies below it, the next float above it
-            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
-                outp.x = __fsub_rn(outp.x, __fmul_rn(dx, 0.5f));
-                outp.y = __fsub_rn(outp.y, __fmul_rn(dy, 0.5f));
-                break;
-            }
-            pdx = dx; pdy = dy;
-#ifdef KLT_LK_TIMELINE
-            if constexpr (LONG) {
-                if (L.flags & 0x200) {
-                    const long long tq6 = clock64();
-                    ph[0] += tq1 - tq0; ph[1] += tq2 - tq1; ph[2] += tq3 - tq2; ph[3] += tq4 - tq3; ph[4] += tq5 - tq4; ph[5] += tq6 - tq5;
-                }
-            }
-#endif
-        }
-
-        if (handed) break;   // (no early return: the warp collectives above must stay provably convergent)
-
-        // ---- err at level 0 ------------------------------------------------------------------------------------
-        if (status && level == 0 && (L.flags & KLT_OPTFLOW_LK_GET_MIN_EIGENVALS) == 0) {
-            const float qx = __fsub_rn(outp.x, hwx), qy = __fsub_rn(outp.y, hwy);
-            int iqx, iqy;
-            if (!floor_in_range(qx, qy, WW, WH, lw, lh, iqx, iqy)) {
-                status = 0;
-                continue;
-            }
-            ensure_j(iqx, iqy);
-            int v00, v01, v10, v11;
-            q14_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), v00, v01, v10, v11);
-            const uint32_t W0 = (uint32_t)(v00 & 0xffff) | ((uint32_t)v01 << 16);
-            const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
-            int e = 0, z1 = 0, z2 = 0;
-            {
-                const int cb = (iqy - jy0) * C::SJ + (iqx - jax);
-                const uint32_t* __restrict__ jbase = reinterpret_cast<const uint32_t*>(jreg) + (cb >> 2);
-                const int sh = (cb & 3) * 8;
-#pragma unroll
-                for (int k = 0; k < C::UPT; ++k) {
-                    const uint32_t* __restrict__ r0 = jbase + jw[k];
-                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
-                    const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
-                    const uint32_t a0 = __funnelshift_r(p0, p1, sh), b0 = __funnelshift_rc(p0, p1, sh + 8);
-                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_rc(q0, q1, sh + 8);
-                    int jv[4];
-                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
-                    jv[1] = dp2a_lo(W1, b1, dp2a_lo(W0, b0, 256)) >> 9;
-                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
-                    jv[3] = dp2a_hi(W1, b1, dp2a_hi(W0, b0, 256)) >> 9;
                     const bool ok = unit_ok(k);
                     const int x0 = unit_x0(k);
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) e += (ok && (x0 + jj) < WW) ? abs(jv[jj] - pxs[k][jj].iv()) : 0;
                 }
+                e = __reduce_add_sync(kFull, e);
+                if (lane == 0) red3[wip] = make_int4(e, 0, 0, 0);
+            } else {
+                // invalid pixels carry gx = gy = 0, so they drop out of all sums without a select
+                int s1 = 0, s2 = 0;
+                unsigned bx = 0, by = 0;
+#pragma unroll
+                for (int k = 0; k < C::UPT; ++k) {
+                    const uint32_t* __restrict__ r0 = jbase + jw[k];
+                    const uint32_t* __restrict__ r1 = r0 + C::SJ / 4;
+                    const uint32_t p0_ = r0[0], p1_ = r0[1], q0 = r1[0], q1 = r1[1];
+                    const uint32_t a0 = __funnelshift_r(p0_, p1_, sh), b0 = __funnelshift_rc(p0_, p1_, sh + 8);
+                    const uint32_t a1 = __funnelshift_r(q0, q1, sh), b1_ = __funnelshift_rc(q0, q1, sh + 8);
+                    int jv[4];
+                    jv[0] = dp2a_lo(W1, a1, dp2a_lo(W0, a0, 256)) >> 9;
+                    jv[1] = dp2a_lo(W1, b1_, dp2a_lo(W0, b0, 256)) >> 9;
+                    jv[2] = dp2a_hi(W1, a1, dp2a_hi(W0, a0, 256)) >> 9;
+                    jv[3] = dp2a_hi(W1, b1_, dp2a_hi(W0, b0, 256)) >> 9;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int d = jv[jj] - pxs[k][jj].iv();
+                        dd[k].set(jj, d);
+                        const int u1 = d * pxs[k][jj].gx(), u2 = d * pxs[k][jj].gy();
+                        s1 += u1; s2 += u2;
+                        bx += (unsigned)abs(u1); by += (unsigned)abs(u2);
+                    }
+                }
+                if (!(c_op & F_CLASSES)) {
+                    // per-thread bounds <= UPT*4*8160*4080 < 2^32 for UPT <= 8; clamp so the point totals cannot wrap
+                    bx = min(bx, (1u << 25) / WPP); by = min(by, (1u << 25) / WPP);
+                    s1 = __reduce_add_sync(kFull, s1);
+                    s2 = __reduce_add_sync(kFull, s2);
+                    bx = __reduce_add_sync(kFull, bx);
+                    by = __reduce_add_sync(kFull, by);
+                    if (lane == 0) red3[wip] = make_int4(s1, s2, (int)bx, (int)by);
+                }
             }
-            point_sum3<WPP>(e, z1, z2, red3, par3, wip, lane, bar);
-            // |d| <= 8160 and WW*WH <= 2056 for the instantiated windows: e <= 2^24, so OpenCV's float32 running sum is exact
-            err = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * WW * WH));
+        }
+        if (op == OP_TIER1 || (op == OP_ITER && (c_op & F_CLASSES))) {
+            // class sums (4 SIMD lanes + tail) of d*gx, d*gy and of the bound |d| * max(|gx|,|gy|) in units of 16
+            int cv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cv[i] = 0;
+#pragma unroll
+            for (int k = 0; k < C::UPT; ++k) {
+                int u1[4], u2[4], ub[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int d = dd[k].get(jj);
+                    const int gx = pxs[k][jj].gx(), gy = pxs[k][jj].gy();
+                    u1[jj] = d * gx;
+                    u2[jj] = d * gy;
+                    ub[jj] = (abs(d) * max(abs(gx), abs(gy)) + 15) >> 4;
+                }
+                const bool tail = unit_x0(k) >= C::NV;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    cv[jj] += tail ? 0 : u1[jj];
+                    cv[5 + jj] += tail ? 0 : u2[jj];
+                    cv[10 + jj] += tail ? 0 : ub[jj];
+                }
+                cv[4] += tail ? (u1[0] + u1[1] + u1[2] + u1[3]) : 0;
+                cv[9] += tail ? (u2[0] + u2[1] + u2[2] + u2[3]) : 0;
+                cv[14] += tail ? (ub[0] + ub[1] + ub[2] + ub[3]) : 0;
+            }
+#pragma unroll
+            for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (1 << 22) / WPP);
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 15; ++i) {
+                const int t = __reduce_add_sync(kFull, cv[i]);
+                mine = (lane == i) ? t : mine;
+            }
+            if (lane < 15) red16[lane * 4 + wip] = mine;
+        } else if (op == OP_REPLAY) {
+            // tier 2: serial replay in OpenCV's order (pairs (l, l+4) summed in int32 first; A.5)
+            int* buf = reinterpret_cast<int*>(dreg);
+            if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }  // pads survive until the next level
+#pragma unroll
+            for (int k = 0; k < C::UPT; ++k)
+                if (unit_ok(k)) {
+                    const int y = unit_y(k), x0 = unit_x0(k);
+                    if (x0 >= C::NV) {
+                        float* tf = reinterpret_cast<float*>(buf) + 8 * CH::SLEN + y * CH::TL + (x0 - C::NV);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (x0 + jj < WW) {
+                                const int d = dd[k].get(jj);
+                                tf[jj] = (float)(d * pxs[k][jj].gx());
+                                tf[CH::TLEN + jj] = (float)(d * pxs[k][jj].gy());
+                            }
+                    } else {
+                        int* si = buf + (y * CH::NS + (x0 >> 3)) * 2 + ((x0 >> 2) & 1);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int d = dd[k].get(jj);
+                            si[jj * CH::SLEN] = d * pxs[k][jj].gx();
+                            si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
+                        }
+                    }
+                }
+            team_sync<WPP>(barC);
+            replay_b<WW, WH, WPP>(buf, wip, lane);
+        } else if (op == OP_GREPLAY) {
+            // serial replay of the G sums in OpenCV's order (A.5): every thread stores the float products of its pixels in
+            // chain order; the scratch (dreg) is dead here
+            float* gf = reinterpret_cast<float*>(dreg);
+#pragma unroll
+            for (int k = 0; k < C::UPT; ++k)
+                if (unit_ok(k)) {
+                    const int y = unit_y(k), x0 = unit_x0(k);
+                    const bool tail = x0 >= C::NV;
+                    float* g0 = tail ? gf + 12 * CH::GQ4 + y * CH::TL + (x0 - C::NV) : gf + y * (C::NV / 4) + (x0 >> 2);
+                    const int sj = tail ? 1 : CH::GQ4;            // next pixel: next element of the tail / next lane chain
+                    const int ss = tail ? CH::GT4 : 4 * CH::GQ4;  // next sum
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (x0 + jj < WW) {
+                            const int gx = pxs[k][jj].gx(), gy = pxs[k][jj].gy();
+                            g0[jj * sj] = (float)(gx * gx);
+                            g0[jj * sj + ss] = (float)(gx * gy);
+                            g0[jj * sj + 2 * ss] = (float)(gy * gy);
+                        }
+                }
+            {   // zero pads
+                constexpr int PQ = CH::GQ4 - CH::GQ, PT = CH::GT4 - CH::GT;
+                if (tid < 12 * PQ) gf[(tid / (PQ > 0 ? PQ : 1)) * CH::GQ4 + CH::GQ + tid % (PQ > 0 ? PQ : 1)] = 0.f;
+                if (tid < 3 * PT) gf[12 * CH::GQ4 + (tid / (PT > 0 ? PT : 1)) * CH::GT4 + CH::GT + tid % (PT > 0 ? PT : 1)] = 0.f;
+            }
+            pads_zeroed = false;   // the G chains overlap the pads of the b chains
+            team_sync<WPP>(barC);
+            replay_g<WW, WH, WPP>(gf, wip, lane);
+        }
+        // ================= partial sums / replay results are in shared memory: hand over to the leader =====================
+        if constexpr (WPP > 1) {
+            if (leader) team_sync<WPP>(barA);
+            else team_arrive<WPP>(barA);
+        } else {
+            __syncwarp();
         }
     }
 
-    if (tid == 0 && !handed) {
-        const long long gid = *reinterpret_cast<volatile long long*>(ws + C::OFF_GID);
+    if (leader && lane == 0) {
         reinterpret_cast<float2*>(L.next_pts)[gid] = outp;
         L.status[gid] = (uint8_t)status;
         L.err[gid] = err;
         if (L.iters) {
             // debug flag 0x100: cycles / 64 in the low 20 bits, tier-1 and tier-2 counts above (profiling aid)
 #ifdef KLT_LK_TIMELINE
-            if (L.flags & 0x400) L.iters[gid] = (int)((t_g0 >> 7) & 0x7fff) | (int)(((gtimer() >> 7) & 0x7fff) << 15) | ((LONG ? 1 : 0) << 30);
-            else if (LONG && (L.flags & 0x200)) L.iters[gid] = (int)(ph[(L.flags >> 12) & 7] >> 2) | (wip << 28);
+            if (L.flags & 0x400) L.iters[gid] = (int)((t_g0 >> 7) & 0x7fff) | (int)(((gtimer() >> 7) & 0x7fff) << 15);
             else
 #endif
             L.iters[gid] = (L.flags & 0x100) ? (int)(((clock64() - t_start) >> 6) & 0xfffff) | (min(n_t1, 63) << 20) | (min(n_t2, 63) << 26) : iters;
         }
     }
-    return !handed;
 }
 
-// Bulk shape: one team of WPP warps per point.  With a work list attached (L.wl), a point that spends L.budget iterations
-// on one level stops there and is pushed onto the list; lk_long_kernel, running beside this kernel, finishes it.
-//
-// Two-phase grid (L.two_phase, the latency shape): the points that bound the launch are almost always border points
-// (their match leaves the frame), and a point found to be long in the last wave would finish a whole long-point latency
-// after the rest.  So the first n_bulk_blocks CTAs only keep the border suspects (everything else is appended to the
-// "normal" list and the CTA exits within a microsecond), and a second range of n_bulk_blocks CTAs serves that list: the
-// hardware dispatches CTAs in index order, so every suspect starts in the first microseconds of the launch and the long
-// ones among them reach the long-point kernel early.  Nothing in phase 1 waits, so the order is a performance
-// assumption only.
+template <int WPP> struct MinBlocks { static constexpr int v = (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)); };
+
 template <int WW, int WH, int WPP>
-__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
+__global__ void __launch_bounds__(kThreads, MinBlocks<WPP>::v)
 lk_fast_kernel(const __grid_constant__ LKLaunch L)
 {
     using C = Cfg<WW, WH, WPP>;
@@ -1044,117 +981,8 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
     const int pic = threadIdx.x / C::NT;        // point within the CTA
     const int tid = threadIdx.x - pic * C::NT;  // thread within the point
     const long long gid = (long long)blockIdx.x * C::PPC + pic;
-    if (gid >= (long long)L.n_per_pair * L.batch) return;  // uniform over the point's warps: its named barrier is never used
-    run_point<WW, WH, WPP, false>(L, gid, nullptr, smem + pic * C::POINT_BYTES, tid, 1 + pic);
-    if (L.wl != nullptr && tid == 0) {
-        __threadfence();            // the work-list entry (if any) is visible before the sign-off
-        atomicAdd(L.wl_ctrl + kCtrlFinished, 1);
-    }
-}
-
-// The two-phase form of the same kernel (see above); a kernel of its own because the divergent waiting code in front of
-// the point makes the compiler wrap every warp collective of the point in convergence barriers.
-template <int WW, int WH, int WPP>
-__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
-lk_fast2p_kernel(const __grid_constant__ LKLaunch L)
-{
-    using C = Cfg<WW, WH, WPP>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int pic = threadIdx.x / C::NT;
-    const int tid = threadIdx.x - pic * C::NT;
-    const int bar = 1 + pic;
-    uint8_t* ws = smem + pic * C::POINT_BYTES;
-    const long long total = (long long)L.n_per_pair * L.batch;
-    long long gid;
-    if ((long long)blockIdx.x < L.n_bulk_blocks) {
-        gid = (long long)blockIdx.x * C::PPC + pic;
-        if (gid >= total) return;
-        const float2 p = reinterpret_cast<const float2*>(L.prev_pts)[gid];
-        const float m = L.suspect_margin;
-        const float w0 = (float)L.prev.lv[0].w - 1.f - m, h0 = (float)L.prev.lv[0].h - 1.f - m;
-        // (votes make the branch conditions warp-uniform for the compiler: otherwise every warp collective of the point is
-        // wrapped in convergence barriers -- 2x the REDUX count and WARPSYNC around each)
-        const bool suspect = __any_sync(kFull, p.x < m || p.y < m || p.x > w0 || p.y > h0);
-        if (tid == 0) {
-            if (!suspect) L.nl[atomicAdd(L.wl_ctrl + kCtrlNormal, 1)] = (int)gid;
-            __threadfence();
-            atomicAdd(L.wl_ctrl + kCtrlDecided, 1);
-        }
-        if (!suspect) return;
-    } else {
-        const long long e = ((long long)blockIdx.x - L.n_bulk_blocks) * C::PPC + pic;
-        if (e >= total) return;
-        volatile int* ctrl = L.wl_ctrl;
-        int spins = 0;
-        while (__any_sync(kFull, ctrl[kCtrlDecided] < total) && ++spins < (1 << 24)) __nanosleep(100);   // every thread polls: uniform control flow
-        __threadfence();
-        const int n_normal = ctrl[kCtrlNormal];   // final once every phase-1 CTA has decided
-        if (__any_sync(kFull, e >= n_normal)) return;
-        gid = __ldcg(L.nl + e);
-    }
-    run_point<WW, WH, WPP, false>(L, gid, nullptr, ws, tid, bar);
-    if (tid == 0) {
-        __threadfence();            // the work-list entry (if any) is visible before the sign-off
-        atomicAdd(L.wl_ctrl + kCtrlFinished, 1);
-    }
-}
-
-// Long points: one CTA of 4 warps per work-list entry (entries e, e + gridDim.x, ...), tuned for the latency of one
-// iteration instead of throughput (launch bounds leave the registers for the pipelined replay).  The kernel may run
-// beside the bulk kernel (side stream): a CTA waits until its entry exists or every bulk point has signed off -- the
-// bulk path never waits for this kernel, so there is no cyclic dependency; a bounded spin turns a missing bulk launch
-// into an early exit instead of a hang.  The last CTA to leave zeroes the control words for the next launch.
-template <int WW, int WH>
-__global__ void __launch_bounds__(kThreads, 4)   // 128 registers: one CTA of this kernel + 4 of the bulk kernel fill an SM's register file
-lk_long_kernel(const __grid_constant__ LKLaunch L)
-{
-    using C = Cfg<WW, WH, 4>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ int have_s;
-    const int tid = threadIdx.x;
-    const long long total = (long long)L.n_per_pair * L.batch;
-    volatile int* ctrl = L.wl_ctrl;
-    for (long long e = blockIdx.x;; e += gridDim.x) {
-        if (tid == 0) {
-            int have = 0;
-            for (long long spins = 0; spins < (1LL << 24); ++spins) {
-                const long long done = ctrl[kCtrlFinished];
-                __threadfence();
-                const long long cnt = ctrl[kCtrlPushed];   // read after `done`: final once done == total
-                if (cnt > e) { have = 1; break; }
-                if (done >= total) break;
-                __nanosleep(100);
-            }
-            __threadfence();
-            have_s = have;
-        }
-        __syncthreads();
-        const int have = have_s;
-        __syncthreads();
-        if (!have) break;
-        LKResume r;
-        {
-            const int4* src = reinterpret_cast<const int4*>(L.wl + e);
-            const volatile int* ep = reinterpret_cast<const volatile int*>(src + 2) + 3;
-            for (int spins = 0; *ep != L.epoch && spins < (1 << 22); ++spins) {}   // the producer is between counter and payload
-            __threadfence();
-            const int4 a = __ldcg(src), b = __ldcg(src + 1), c = __ldcg(src + 2);
-            r.gid = ((long long)(unsigned)a.x) | ((long long)a.y << 32);
-            r.level = a.z; r.j = a.w;
-            r.nx = __int_as_float(b.x); r.ny = __int_as_float(b.y); r.pdx = __int_as_float(b.z); r.pdy = __int_as_float(b.w);
-            r.iters = c.x; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-        }
-        run_point<WW, WH, 4, true>(L, r.gid, &r, smem, tid, 1);
-        __syncthreads();   // the next entry reuses the scratch
-    }
-    if (tid == 0) {
-        const int gone = atomicAdd(L.wl_ctrl + kCtrlLongGone, 1);
-        if (gone == (int)gridDim.x - 1) {
-            L.wl_ctrl[kCtrlPushed] = 0; L.wl_ctrl[kCtrlNormal] = 0; L.wl_ctrl[kCtrlDecided] = 0; L.wl_ctrl[kCtrlFinished] = 0;
-            __threadfence();
-            L.wl_ctrl[kCtrlLongGone] = 0;
-        }
-    }
+    if (gid >= (long long)L.n_per_pair * L.batch) return;  // uniform over the point's warps: its named barriers are never used
+    run_point<WW, WH, WPP>(L, gid, smem + pic * C::POINT_BYTES, tid, 1 + 3 * pic);
 }
 
 template <int WW, int WH, int WPP>
@@ -1163,88 +991,27 @@ klt_status launch_fast(const LKLaunch& L, cudaStream_t stream)
     using C = Cfg<WW, WH, WPP>;
     static_assert(WW * WH <= 2056, "err pass assumes an exact float32 sum");
     static_assert(C::UPT <= 8, "per-thread bound accumulators would overflow");
+    static_assert(1 + 3 * C::PPC <= 16, "named barriers per CTA");
     static PerDeviceOnce configured;
     const size_t smem = (size_t)C::POINT_BYTES * C::PPC;
     if (configured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(lk_fast_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(lk_fast2p_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = cudaFuncSetAttribute(lk_fast_kernel<WW, WH, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (klt_status)e;
     }
-    if (L.n_per_pair < 0) return KLT_OK;   // configure only (loads the kernel before anything is launched)
     const long long total = (long long)L.n_per_pair * L.batch;
     const long long blocks = (total + C::PPC - 1) / C::PPC;
-    if (blocks > 0x3fffffffLL) return KLT_ERR_UNSUPPORTED;
-    LKLaunch K = L;
-    K.n_bulk_blocks = blocks;
-    if (K.two_phase) lk_fast2p_kernel<WW, WH, WPP><<<(unsigned)(2 * blocks), kThreads, smem, stream>>>(K);
-    else lk_fast_kernel<WW, WH, WPP><<<(unsigned)blocks, kThreads, smem, stream>>>(K);
+    if (blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
+    lk_fast_kernel<WW, WH, WPP><<<(unsigned)blocks, kThreads, smem, stream>>>(L);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
 
 template <int WW, int WH>
-klt_status launch_long(const LKLaunch& L, cudaStream_t stream)
+klt_status launch_window(const LKLaunch& L, int wpp, cudaStream_t stream)
 {
-    using CL = Cfg<WW, WH, 4>;
-    static PerDeviceOnce configured;
-    if (configured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(lk_long_kernel<WW, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL::POINT_BYTES);
-        if (e != cudaSuccess) return (klt_status)e;
-    }
-    if (L.n_per_pair < 0) return KLT_OK;   // configure only
-    lk_long_kernel<WW, WH><<<(unsigned)L.n_resume_blocks, kThreads, (size_t)CL::POINT_BYTES, stream>>>(L);
-    const cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? KLT_OK : (klt_status)e;
-}
-
-template <int WW, int WH>
-klt_status launch_window(const LKLaunch& L, int wpp, bool team_bulk, cudaStream_t stream)
-{
-    LKLaunch K = L;
-    // the team shape hands off on the budget only; the warp shape also when a float32 sum really rounds
-    if (K.budget >= K.max_count) K.budget = 0;
-    const bool handoff = K.wl != nullptr && K.n_resume_blocks > 0 && (K.budget > 0 || !team_bulk);
-    if (!handoff) { K.wl = nullptr; K.wl_ctrl = nullptr; K.nl = nullptr; K.budget = 0; K.n_resume_blocks = 0; }
-    const bool concurrent = handoff && team_bulk && K.budget > 0 && K.two_phase && K.nl && K.side_stream && K.ev_fork && K.ev_join;
-    K.two_phase = concurrent ? 1 : 0;
-    auto launch_bulk = [&](const LKLaunch& B) {
-        if (!team_bulk) return lk_launch_warp(B, stream);
-        if (wpp == 1) return launch_fast<WW, WH, 1>(B, stream);
-        if (wpp == 2) return launch_fast<WW, WH, 2>(B, stream);
-        return launch_fast<WW, WH, 4>(B, stream);
-    };
-    if (concurrent) {
-        // Both kernels are configured (and thereby loaded) before either is launched: loading a kernel can synchronise
-        // the device, and the long-point kernel would sit in its bounded spin meanwhile.  The bulk kernel is launched
-        // first; the long-point kernel follows on the high-priority side stream, so its CTAs (one per SM) take the first
-        // slots the bulk frees -- within a microsecond, because the non-suspect CTAs of phase 1 leave at once.
-        LKLaunch cfg = K;
-        cfg.n_per_pair = -1;
-        klt_status s = launch_bulk(cfg);
-        if (s == KLT_OK) s = launch_long<WW, WH>(cfg, stream);
-        if (s != KLT_OK) return s;
-        cudaStream_t side = static_cast<cudaStream_t>(K.side_stream);
-        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(K.ev_fork), stream);
-        if (e != cudaSuccess) return (klt_status)e;
-        s = launch_bulk(K);
-        if (s != KLT_OK) return s;
-        // from here on a failure leaves the bulk's long points unfinished (the caller sees the error) and the control
-        // words dirty: they are cleared behind the bulk kernel so that the next launch starts clean
-        e = cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(K.ev_fork), 0);
-        if (e == cudaSuccess) {
-            s = launch_long<WW, WH>(K, side);
-            if (s == KLT_OK) {
-                e = cudaEventRecord(static_cast<cudaEvent_t>(K.ev_join), side);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(K.ev_join), 0);
-                if (e == cudaSuccess) return KLT_OK;
-            }
-        }
-        cudaMemsetAsync(K.wl_ctrl, 0, 64, stream);
-        return s != KLT_OK ? s : (klt_status)e;
-    }
-    klt_status s = launch_bulk(K);
-    if (s != KLT_OK || !handoff) return s;
-    return launch_long<WW, WH>(K, stream);
+    if (wpp == 1) return launch_fast<WW, WH, 1>(L, stream);
+    if (wpp == 2) return launch_fast<WW, WH, 2>(L, stream);
+    return launch_fast<WW, WH, 4>(L, stream);
 }
 
 }  // namespace
@@ -1253,16 +1020,12 @@ klt_status launch_window(const LKLaunch& L, int wpp, bool team_bulk, cudaStream_
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream)
 {
     const long long total = (long long)L.n_per_pair * L.batch;
-    // Bulk shape: teams of WPP warps per point, patch in registers: 31x31 -> 4 warps; 21x21 -> 4 while the points fit
-    // the chip about once, else 2 (KLT_LK_WPP forces it).  KLT_LK_SHAPE=warp selects the one-warp-per-point shape of
-    // klt_lk_warp.cu for A/B runs (measured slower on B200).
-    static const char* shape = getenv("KLT_LK_SHAPE");
-    const bool team_bulk = !(shape && shape[0] == 'w');
+    // warps per point: 31x31 -> 4; 21x21 -> 4 while the points fit the chip about once, else 2 (KLT_LK_WPP forces it)
     int wpp = 4;
     if (L.win_w * L.win_h <= 21 * 21 && total > (long long)sm_count * 32) wpp = 2;
     if (forced_wpp == 1 || forced_wpp == 2 || forced_wpp == 4) wpp = forced_wpp;
-    if (L.win_w == 21 && L.win_h == 21) return launch_window<21, 21>(L, wpp, team_bulk, stream);
-    if (L.win_w == 31 && L.win_h == 31) return launch_window<31, 31>(L, wpp, team_bulk, stream);
+    if (L.win_w == 21 && L.win_h == 21) return launch_window<21, 21>(L, wpp, stream);
+    if (L.win_w == 31 && L.win_h == 31) return launch_window<31, 31>(L, wpp, stream);
     return KLT_ERR_UNSUPPORTED;
 }
 
