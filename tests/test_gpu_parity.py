@@ -149,13 +149,13 @@ def test_lk_bit_exact_vs_oracle_and_cv2(klt, oracle, cv2, case):
     assert_lk_equal(got, ref, "vs cv2")
 
 
-@pytest.mark.parametrize("wpp", ["1", "2", "4"])
+@pytest.mark.parametrize("wpp", ["1", "2", "4"], ids=["slots1", "slots2", "slots4"])
 def test_lk_team_sizes_bit_exact(klt, wpp):
     """Every team size of the specialised kernel (leader warp + 0, 1 or 3 follower warps per keypoint) ships in the
-    library and is picked by window / point count: same bit-exactness bar for each, forced through KLT_LK_WPP."""
+    library and is picked by window / point count: same bit-exactness bar for each, forced through KLT_LK_SLOTS."""
     import os, subprocess, sys
     e = dict(os.environ)
-    e["KLT_LK_WPP"] = wpp
+    e["KLT_LK_SLOTS"] = wpp
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lk_variant_check.py")], env=e,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
