@@ -45,7 +45,12 @@ typedef int klt_status;
 #define KLT_ERR_OUT_OF_MEMORY (-4)
 #define KLT_ERR_INTERNAL (-5)
 
-typedef struct klt_ctx klt_ctx; /* opaque: device id, stream, workspaces, pinned staging */
+/* Opaque context: device id, two streams, device workspace, pinned staging, helper threads for pageable inputs.
+ * Threads: a context may be shared.  The *_host entry points use the context's workspaces and streams and are
+ * serialised by a mutex inside the context (concurrent callers queue up; one context per thread avoids that).  The
+ * device-pointer entry points keep no per-call state in the context and may run concurrently on different streams.
+ * Every entry point makes the context's device current for the duration of the call and restores the caller's. */
+typedef struct klt_ctx klt_ctx;
 
 /* One pyramid level as the kernels see it (row `y` of batch item `b` starts at
  * data + b*batch_stride + y*pitch). */
@@ -124,7 +129,9 @@ klt_status klt_lk_track(klt_ctx* ctx,
 /* cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, winSize, maxLevel, criteria[, flags,
  * minEigThreshold]) -> nextPts, status, err.  HOST buffers (pinned or pageable); images u8 with
  * arbitrary row pitch; points float32 [n][2].  Synchronous.  top_level_out (optional) receives the
- * last pyramid level used. */
+ * last pyramid level used.  Pinned images are DMA'd in place; pageable ones (numpy arrays of the un-edited
+ * reference) are staged through a pinned landing zone by the calling thread and three helper threads of the
+ * context while the DMA of the first image already runs. */
 klt_status klt_calc_optical_flow_pyr_lk_host(klt_ctx* ctx,
                         const uint8_t* prev_img, int64_t prev_pitch,
                         const uint8_t* next_img, int64_t next_pitch, int w, int h,

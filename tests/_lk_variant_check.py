@@ -1,4 +1,4 @@
-"""Run in a fresh process with KLT_LK_SLOTS set (the library reads it once): every team size of the specialised LK kernel
+"""Run in a fresh process with KLT_LK_WPP set (the library reads it once): every team size of the specialised LK kernel
 (1, 2 or 4 warps per keypoint; the default picks by window and point count) must stay
 bit-identical to live cv2.  Used by tests/test_gpu_parity.py::test_lk_team_sizes_bit_exact."""
 import os

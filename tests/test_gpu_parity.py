@@ -149,13 +149,13 @@ def test_lk_bit_exact_vs_oracle_and_cv2(klt, oracle, cv2, case):
     assert_lk_equal(got, ref, "vs cv2")
 
 
-@pytest.mark.parametrize("wpp", ["1", "2", "4"], ids=["slots1", "slots2", "slots4"])
+@pytest.mark.parametrize("wpp", ["1", "2", "4"], ids=["wpp1", "wpp2", "wpp4"])
 def test_lk_team_sizes_bit_exact(klt, wpp):
-    """Every team size of the specialised kernel (leader warp + 0, 1 or 3 follower warps per keypoint) ships in the
-    library and is picked by window / point count: same bit-exactness bar for each, forced through KLT_LK_SLOTS."""
+    """Every team size of the specialised kernel (1, 2 or 4 warps per keypoint) ships in the library and is picked by
+    window / point count: same bit-exactness bar for each, forced through KLT_LK_WPP."""
     import os, subprocess, sys
     e = dict(os.environ)
-    e["KLT_LK_SLOTS"] = wpp
+    e["KLT_LK_WPP"] = wpp
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lk_variant_check.py")], env=e,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -379,3 +379,86 @@ def test_second_device_in_the_same_process(klt, cv2):
         assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, device=dev, **lk), ref, "device %d" % dev)
         got = klt.goodFeaturesToTrack(a, 1000, 0.03, 10, blockSize=31, device=dev)
         assert got.shape == refc.shape and np.array_equal(got, refc)
+
+
+# ---------------------------------------------------------------- host-path properties of round 2 -----------
+def test_pageable_and_pinned_inputs_give_the_same_results(klt, cv2):
+    """Pageable numpy arrays (what the un-edited reference passes: loader.py:86, pipeline.py:103) are staged by the helper
+    threads of the context, pinned ones are DMA'd in place; odd sizes exercise the slice boundaries of the staging copy."""
+    lk = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    for (h, w, n) in [(376, 1241, 700), (601, 1000, 300), (768, 1024, 300)]:
+        a, b = S.frame_pair(h, w, seed=h)
+        p = S.uniform_points(n, h, w, seed=w)
+        ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, **lk)
+        pa, pb, pp = klt.pinned_empty(a.shape), klt.pinned_empty(b.shape), klt.pinned_empty(p.shape, np.float32)
+        pa[...] = a; pb[...] = b; pp[...] = p
+        for _ in range(3):      # the helpers are started by the first call, asleep or spinning afterwards
+            assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, **lk), ref, "pageable %dx%d" % (w, h))
+        assert_lk_equal(klt.calcOpticalFlowPyrLK(pa, pb, pp, None, **lk), ref, "pinned %dx%d" % (w, h))
+        assert_lk_equal(klt.calcOpticalFlowPyrLK(a, pb, p, None, **lk), ref, "mixed %dx%d" % (w, h))
+    import time
+    time.sleep(0.01)            # helpers have gone to sleep on their condition variable: the next job wakes them
+    assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, **lk), ref, "after sleep")
+
+
+def test_concurrent_callers_share_one_context(klt, cv2):
+    """A klt_ctx serialises its *_host entry points internally (include/klt_b200.h): threads calling the drop-in at the
+    same time get the same results as sequential calls."""
+    import threading
+    lk = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    jobs = []
+    for i in range(4):
+        a, b = S.frame_pair(240, 320 + 16 * i, seed=40 + i)
+        p = S.uniform_points(200, 240, 320 + 16 * i, seed=50 + i)
+        jobs.append((a, b, p, cv2.calcOpticalFlowPyrLK(a, b, p, None, **lk)))
+    errors = []
+
+    def work(job):
+        try:
+            for _ in range(20):
+                assert_lk_equal(klt.calcOpticalFlowPyrLK(job[0], job[1], job[2], None, **lk), job[3])
+        except Exception as ex:   # noqa: BLE001
+            errors.append(ex)
+    ts = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:1]
+
+
+def test_tracker_owns_its_frames(klt, cv2, torch_cuda):
+    """KLTTracker copies every frame into storage of its own: the caller may upload frame t+1 into the SAME device tensor."""
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    lk = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    frames = S.sequence(120, 160, 4, seed=77)
+    p = S.uniform_points(60, 120, 160, seed=5)
+    buf = torch.from_numpy(frames[0]).cuda()
+    trk = T.KLTTracker(**lk).reset(buf)
+    cur = p.copy()
+    for t in range(1, len(frames)):
+        buf.copy_(torch.from_numpy(frames[t]))            # overwrites what reset() / the last track() was given
+        q, st, er = trk.track(buf, torch.from_numpy(cur.reshape(1, -1, 2)).cuda())
+        ref = cv2.calcOpticalFlowPyrLK(frames[t - 1], frames[t], cur, None, **lk)
+        assert_lk_equal((q.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy()), ref, "frame %d" % t)
+        cur = ref[0]
+
+
+def test_calls_do_not_change_the_current_device(klt, torch_cuda):
+    """The C ABI makes its context's device current for the duration of a call only."""
+    torch = torch_cuda
+    a, b = S.frame_pair(120, 160, seed=3)
+    p = S.uniform_points(30, 120, 160, seed=4)
+    before = torch.cuda.current_device()
+    klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=2, device=0)
+    klt.goodFeaturesToTrack(a, 100, 0.03, 10, blockSize=15, device=0)
+    assert torch.cuda.current_device() == before
+    if torch.cuda.device_count() >= 2:
+        from visual_odom_pipeline_b200 import tracker as T
+        klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=2, device=1)
+        assert torch.cuda.current_device() == before
+        # device-pointer entry points on tensors of cuda:1 while cuda:0 is current
+        ta, tb = torch.from_numpy(a).to("cuda:1"), torch.from_numpy(b).to("cuda:1")
+        q, st, er = T.calc_optical_flow_pyr_lk_device(ta, tb, torch.from_numpy(p).to("cuda:1"), None, winSize=(21, 21), maxLevel=2)
+        ref = klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=2, device=0)
+        assert_lk_equal((q.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy()), ref)
+        assert torch.cuda.current_device() == before

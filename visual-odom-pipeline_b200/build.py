@@ -82,7 +82,8 @@ def build(force=False, verbose=False, variant=None, extra=None):
             sys.stderr.write(log)
         if rc != 0:
             raise RuntimeError("nvcc failed compiling for %s" % os.path.basename(obj))
-    res = subprocess.run([nvcc(), "-shared", "-cudart", "static", "-o", lib] + [r[0] for r in results], capture_output=True, text=True)
+    res = subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", lib] + [r[0] for r in results],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking %s" % os.path.basename(lib))

@@ -644,7 +644,7 @@ klt_status lk_launch(const LKLaunch& L, int sm_count, cudaStream_t stream)
     if (L.win_w <= 2 || L.win_h <= 2) return KLT_ERR_INVALID_ARG;
     {   // specialised kernels for the common windows; KLT_LK_GENERIC=1 forces the generic one (tests)
         static const char* force_generic = getenv("KLT_LK_GENERIC");
-        static const char* force_wpp = getenv("KLT_LK_SLOTS");
+        static const char* force_wpp = getenv("KLT_LK_WPP");
         if (!(force_generic && force_generic[0] == '1')) {
             const klt_status s = lk_launch_fast(L, sm_count, force_wpp ? atoi(force_wpp) : 0, stream);
             if (s != KLT_ERR_UNSUPPORTED) return s;

@@ -47,12 +47,20 @@ def alloc_image_batch(batch, h, w, device="cuda"):
 
 
 class DevicePyramid:
-    """Gaussian pyramid of a batch of images on the device (levels >= 1 in one buffer)."""
+    """Gaussian pyramid of a batch of images on the device (levels >= 1 in one buffer).
 
-    def __init__(self, images, winSize=(21, 21), maxLevel=3, ctx=None, out=None):
+    Level 0 is the caller's tensor itself unless `copy=True`: without a copy the caller must leave the tensor unmodified
+    for as long as the pyramid is used (levels 1..top would otherwise belong to another image than level 0).
+    `copy=True` moves level 0 into storage owned by the pyramid (128-byte pitch: the kernels' 128-bit load path)."""
+
+    def __init__(self, images, winSize=(21, 21), maxLevel=3, ctx=None, out=None, copy=False):
         torch = _torch()
         win_w, win_h, maxLevel = _check_win_level(winSize, maxLevel)
         self.images = _as_image_batch(images)
+        if copy:
+            own = alloc_image_batch(self.images.shape[0], self.images.shape[1], self.images.shape[2], device=self.images.device)
+            own.copy_(self.images)
+            self.images = own
         B, H, W = self.images.shape
         self.ctx = ctx or _lib.default_context(self.images.device.index or 0)
         self.win = (win_w, win_h)
@@ -186,7 +194,9 @@ class KLTTracker:
     Caller-side fusion of the reference's tracking step (src/extractor/extractor.py:38-88 and
     src/pipeline/pipeline.py:98-103): the reference calls cv2.calcOpticalFlowPyrLK four times per
     frame on the same image pair, i.e. OpenCV builds 8 pyramids per frame; here each frame's pyramid
-    is built exactly once and reused as the next pair's `prev`.
+    is built exactly once and reused as the next pair's `prev`.  The tracker copies every frame into storage of its
+    own, so the caller may overwrite its frame tensor (e.g. upload frame t+1 into the same buffer) as soon as a call
+    returns.
     """
 
     def __init__(self, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03), flags=0, minEigThreshold=1e-4):
@@ -195,7 +205,7 @@ class KLTTracker:
         self.prev = None
 
     def reset(self, images):
-        self.prev = DevicePyramid(images, self.winSize, self.maxLevel)
+        self.prev = DevicePyramid(images, self.winSize, self.maxLevel, copy=True)
         return self
 
     def track(self, images, prevPts, bidirectional=False):
@@ -205,7 +215,7 @@ class KLTTracker:
         started from the forward result) and returns it as a 4th output."""
         if self.prev is None:
             raise error("klt_b200: KLTTracker.track() before reset()")
-        nxt = DevicePyramid(images, self.winSize, self.maxLevel, ctx=self.prev.ctx)
+        nxt = DevicePyramid(images, self.winSize, self.maxLevel, ctx=self.prev.ctx, copy=True)
         out = lk_track(self.prev, nxt, prevPts, None, self.criteria, self.flags, self.minEigThreshold)
         if bidirectional:
             back = lk_track(self.prev, nxt, out[0], None, self.criteria, self.flags, self.minEigThreshold)
@@ -243,7 +253,7 @@ class KLTTracker:
             survivors = p1[0][keep[0]]
             keep = keep[0]
         else:
-            self.prev = DevicePyramid(img, self.winSize, self.maxLevel, ctx=self.prev.ctx if self.prev is not None else None)
+            self.prev = DevicePyramid(img, self.winSize, self.maxLevel, ctx=self.prev.ctx if self.prev is not None else None, copy=True)
             survivors = torch.zeros((0, 2), dtype=torch.float32, device=img.device)
             keep = torch.zeros((0,), dtype=torch.bool, device=img.device)
         H, W = img.shape[1], img.shape[2]
