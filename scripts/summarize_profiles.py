@@ -19,7 +19,7 @@ for f in os.listdir(src):
 
 
 def short(name):
-    for key in ("lk_fast_kernel", "lk_kernel", "pyr_down_ring_kernel", "pyr_down_tma_kernel", "pyr_down_kernel", "repitch_kernel",
+    for key in ("lk_fast_kernel", "lk_kernel", "pyr_build_fused_kernel", "pyr_down_ring_kernel", "pyr_down_tma_kernel", "pyr_down_kernel", "repitch_kernel",
                 "track_filter_kernel", "cov_kernel", "row_scan_kernel", "row_sum_small_kernel", "col_scan_kernel", "candidates_kernel",
                 "rank_keys_kernel", "scatter_keys_kernel"):
         if key in name:
@@ -141,6 +141,13 @@ for rep in sorted(os.listdir(src)):
             "sm_active_cycles_avg": num(d, "smsp__cycles_active.avg"), "sm_elapsed_cycles_max": num(d, "sm__cycles_elapsed.max"),
         }
         counters.setdefault(rep.replace(".ncu-rep", ""), []).append(entry)
+# bench.py quotes these figures only for the kernel sources they were captured on
+sys.path.insert(0, os.path.dirname(here))
+try:
+    import bench
+    counters["csrc_sha16"] = bench.csrc_sha16()
+except Exception as ex:   # pragma: no cover
+    counters["csrc_sha16"] = "unknown (%r)" % ex
 with open(os.path.join(dst, "counters.json"), "w") as f:
     json.dump(counters, f, indent=1)
 print("wrote", sorted(os.listdir(dst)))
