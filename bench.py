@@ -374,6 +374,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_cores = sharding.bind_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dev = torch.device("cuda", local_rank)
     ctx = K.default_context(local_rank)
     L = _lib.load()
@@ -666,7 +667,8 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": describe(wl_name, wl),
                        "l2": "rotating pool of %d distinct device-resident pairs (%.0f MB) > 126 MB L2; no flush needed" % (P, P * pair_bytes / 1e6),
-                       "sharding": "each rank tracks its own independent sequences; no collective on the data path"},
+                       "sharding": "each rank tracks its own independent sequences; no collective on the data path",
+                       "host_cores_per_rank": len(host_cores)},
             "timing": {"blocks": n_blocks, "steps_per_block": K_steps, "block_ms": block_ms,
                        "note": "value / ms_per_step / e2e = median block of exactly `steps` steps; blocks are added until >= %d steps are timed" % MIN_TIMED_STEPS},
             "pairs_per_sec": world * K_steps / (dev_ms * 1e-3),

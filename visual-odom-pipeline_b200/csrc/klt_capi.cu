@@ -87,6 +87,8 @@ klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
     bytes = align_up(bytes + bytes / 4, 1 << 20);
     cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    // padding columns / rows of the workspace are read (never used) by the 16-byte granule copies: define them once
+    if (cudaMemset(ctx->d_ws, 0, bytes) != cudaSuccess) cudaGetLastError();
     ctx->d_ws_bytes = bytes;
     return KLT_OK;
 }

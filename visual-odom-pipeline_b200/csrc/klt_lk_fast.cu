@@ -571,6 +571,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 // order; all scratch is dead here (every warp passed the exchange barrier above)
                 using CH = Chains<WW, WH>;
                 float* gf = reinterpret_cast<float*>(dreg);
+                if constexpr (WPP == 1) __syncwarp();   // one warp: the border path's reads of dreg are ordered before these stores
 #pragma unroll
                 for (int k = 0; k < C::UPT; ++k)
                     if (unit_ok(k)) {
@@ -732,6 +733,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     ++n_t2;
                     using CH = Chains<WW, WH>;
                     int* buf = reinterpret_cast<int*>(dreg);
+                    if constexpr (WPP == 1) __syncwarp();   // one warp: earlier readers of the scratch (border path, last replay) first
                     if (!pads_zeroed) { zero_pad_b<WW, WH, C::NT>(buf, tid); pads_zeroed = true; }  // pads survive until the next level
 #pragma unroll
                     for (int k = 0; k < C::UPT; ++k)

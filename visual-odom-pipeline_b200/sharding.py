@@ -44,6 +44,23 @@ def init_process_group(backend=None):
     return rank, local_rank, world
 
 
+def bind_rank_to_cores(local_rank, local_world):
+    """Give every rank of one box its own contiguous slice of the host cores (the ranks' Python threads, the helper
+    threads of the pageable path and the driver's threads then stop migrating over each other: with 8 processes on one
+    host the end-to-end path lost 19 % to that in round 1).  No-op for a single rank or where affinity is unsupported.
+    -> the cores this process may use now"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(cores) < 2 * local_world:
+            return cores
+        per = len(cores) // local_world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return []
+
+
 def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

@@ -42,7 +42,7 @@ def alloc_image_batch(batch, h, w, device="cuda"):
     kernel takes its 128-bit load path (a plain contiguous tensor with odd W falls back to byte loads)."""
     torch = _torch()
     pitch = (w + 127) // 128 * 128
-    store = torch.empty((batch, h, pitch), dtype=torch.uint8, device=device)
+    store = torch.zeros((batch, h, pitch), dtype=torch.uint8, device=device)   # padding columns are read by 16-byte granule copies
     return store[:, :, :w]
 
 
@@ -77,7 +77,8 @@ class DevicePyramid:
                 raise error("klt_b200: pyramid buffer too small")
             self.buffer = out
         else:
-            self.buffer = torch.empty(nbytes, dtype=torch.uint8, device=self.images.device)
+            # zeros: the pitch padding of a level is read (never used) by the 16-byte granule copies of the next step
+            self.buffer = torch.zeros(nbytes, dtype=torch.uint8, device=self.images.device)
         self.build()
 
     @property
