@@ -622,9 +622,10 @@ def main():
         batched = {"pairs": P, "points": P * n, "ms": bms, "keypoints_per_sec": P * n / (bms * 1e-3), "pairs_per_sec": P / (bms * 1e-3),
                    "int32_mac_frac": (mac_pt * P * n / (bms * 1e-3) / 1e9) / mac_peak}
 
-        detection = None
+        detection = prefilter = None
         if not args.no_detection and h > 31 and w > 31:
             detection = run_detection(args, wl, K, L, hp, hpin, imgs, P, n_host, local_rank, world, dev, stream)
+            prefilter = run_prefilter(args, wl, K, hp, imgs, P, local_rank, world, stream)
 
         # ---- parity spot check of pool entry used first, against live cv2 ------------------------------------
         parity = None
@@ -690,6 +691,7 @@ def main():
             "sharded_batch": sharded,
             "parity": parity,
             "detection": detection,
+            "prefilter": prefilter,
             "cpu_baseline": cpu,
             "device": ctx.name,
         }
@@ -782,6 +784,64 @@ def run_sharded_batch(args, wl, rank, local_rank, world, dev):
             "timed": "per rank: %d batched pyramid builds + %d batched LK launches, device resident (CUDA events, max over ranks, median of 3)"
                      % (n_frames, n_frames - 1),
             "gathered_sequences_bit_identical_to_cv2": {"sample": sample, "ok": bool(ok)}}
+
+
+def run_prefilter(args, wl, K, hp, imgs, P, local_rank, world, stream):
+    """Row f3: the loader's cv2.bilateralFilter(img, 5, 1.5, 1.5) (src/loader/loader.py:16-20,86), once per
+    frame.  Reported next to the headline, not part of `value`."""
+    import torch
+    from visual_odom_pipeline_b200 import filters as F
+    h, w = wl["h"], wl["w"]
+    ref_kw = dict(d=5, sigmaColor=1.5, sigmaSpace=1.5)
+    frames = [np.array(x[0]) for x in hp[:8]]
+    for r_ in range(5):
+        got = K.bilateralFilter(frames[r_ % len(frames)], device=local_rank, **ref_kw)
+    reps = 200
+    t0 = time.perf_counter()
+    for r_ in range(reps):
+        K.bilateralFilter(frames[r_ % len(frames)], device=local_rank, **ref_kw)
+    host_ms = 1e3 * (time.perf_counter() - t0) / reps
+    nb = min(64, 2 * P)
+    src = imgs[:nb, :, :w]
+    dst = torch.empty_like(imgs[:nb])[:, :, :w]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for r_ in range(3):
+        if r_ == 2:
+            ev[0].record(stream)
+        F.bilateral_filter(src, out=dst, **ref_kw)
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    bms = ev[0].elapsed_time(ev[1])
+    out = {"api": "visual_odom_pipeline_b200.bilateralFilter(numpy image, d=5, sigmaColor=1.5, sigmaSpace=1.5) -> numpy",
+           "e2e_ms_per_frame": host_ms, "h2d_bytes_per_frame": w * h, "d2h_bytes_per_frame": w * h,
+           "batched": {"frames": nb, "ms": bms, "us_per_frame": 1e3 * bms / nb, "gbs": 2.0 * nb * w * h / (bms * 1e-3) / 1e9,
+                       "algorithmic_bytes_per_frame": 2 * w * h, "note": "device resident, one launch for the batch (u8 in, u8 out)"}}
+    try:
+        import cv2
+        was = cv2.ipp.useIPP()
+        cv2.ipp.setUseIPP(False)
+        gen = cv2.bilateralFilter(frames[0], **ref_kw)
+        cv2.ipp.setUseIPP(True)
+        ipp = cv2.bilateralFilter(frames[0], **ref_kw)
+        got = K.bilateralFilter(frames[0], device=local_rank, **ref_kw)
+        out["parity"] = {"pixels": int(got.size), "differ_from_opencv_generic_path": int((got != gen).sum()),
+                         "max_abs_diff_vs_generic": int(np.abs(got.astype(int) - gen.astype(int)).max()),
+                         "max_abs_diff_vs_ipp_wheel": int(np.abs(got.astype(int) - ipp.astype(int)).max()),
+                         "ipp_vs_generic_differ_fraction": float((ipp != gen).mean())}
+        if world == 1 and not args.no_cpu_baseline:
+            for name, flag in (("cv2_ipp_ms_per_frame", True), ("cv2_generic_ms_per_frame", False)):
+                cv2.ipp.setUseIPP(flag)
+                for r_ in range(3):
+                    cv2.bilateralFilter(frames[r_ % len(frames)], **ref_kw)
+                t0 = time.perf_counter()
+                for r_ in range(40):
+                    cv2.bilateralFilter(frames[r_ % len(frames)], **ref_kw)
+                out[name] = 1e3 * (time.perf_counter() - t0) / 40
+            out["cv2_threads"] = cv2.getNumThreads()
+        cv2.ipp.setUseIPP(was)
+    except Exception as ex:   # pragma: no cover
+        out["parity"] = {"error": repr(ex)}
+    return out
 
 
 def run_detection(args, wl, K, L, hp, hpin, imgs, P, n_host, local_rank, world, dev, stream):

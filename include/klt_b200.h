@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KLT_B200_VERSION 110 /* 0.1.1: + corner detection */
+#define KLT_B200_VERSION 120 /* 0.1.2: + bilateral pre-filter; thread-safe contexts; pageable inputs staged in the library */
 
 #define KLT_MAX_LEVELS 16   /* pyramid levels incl. level 0 (cv2 stops when a level <= winSize) */
 #define KLT_MAX_WIN_AREA 4096 /* win_w * win_h supported by the LK kernel (cv2 default 21x21) */
@@ -220,6 +220,21 @@ klt_status klt_good_features_to_track_host(klt_ctx* ctx, const uint8_t* img, int
 klt_status klt_good_features_to_track_points_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h,
                         const float* points, int n_points, int mask_radius, int max_corners, double quality_level,
                         double min_distance, int block_size, float* corners, int capacity, int* n_out);
+
+/* ---- bilateral pre-filter ------------------------------------------------------------------
+ * Replaces cv2.bilateralFilter(img, d=5, sigmaColor=1.5, sigmaSpace=1.5) as the reference's loader applies it to every
+ * frame (src/loader/loader.py:16-20,86): 8-bit single channel, BORDER_REFLECT_101 (cv2's default), d <= 15.
+ * Arithmetic: oracle/bilateral_oracle.c B.1-B.6 = OpenCV's own code path (an OpenCV build without IPP); differs from
+ * it only on exact rounding ties (< 1e-5 of the pixels, by 1), and by at most 1 from the IPP-enabled wheel. */
+
+/* Device pointers, batched, asynchronous on `stream`.  d_dst must not alias d_src. */
+klt_status klt_bilateral_filter(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_batch_stride,
+                        uint8_t* d_dst, int64_t dst_pitch, int64_t dst_batch_stride, int batch, int d, double sigma_color,
+                        double sigma_space, void* stream);
+
+/* HOST buffers, synchronous. */
+klt_status klt_bilateral_filter_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h, int d, double sigma_color,
+                        double sigma_space, uint8_t* out, int64_t out_pitch);
 
 #ifdef __cplusplus
 }

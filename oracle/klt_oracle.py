@@ -21,7 +21,7 @@ USE_INITIAL_FLOW, GET_MIN_EIGENVALS = 4, 8
 
 def build(force=False):
     """Compile the oracle with gcc (seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("klt_oracle.c", "gftt_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("klt_oracle.c", "gftt_oracle.c", "bilateral_oracle.c", "Makefile")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
     return _SO
@@ -56,6 +56,9 @@ def lib():
         L.klt_oracle_circle_half_widths.restype = c.c_int
         L.klt_oracle_mask_from_points.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64]
         L.klt_oracle_mask_from_points.restype = c.c_int
+        L.klt_oracle_bilateral_filter.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int64, c.c_int, c.c_double, c.c_double,
+                                                  c.c_int, c.c_int, c.c_void_p, c.c_int64]
+        L.klt_oracle_bilateral_filter.restype = c.c_int
         _lib = L
     return _lib
 
@@ -199,4 +202,18 @@ def mask_from_points(points, radius, shape):
     rc = lib().klt_oracle_mask_from_points(pts.ctypes.data if len(pts) else None, len(pts), int(radius), w, h, out.ctypes.data, w)
     if rc < 0:
         raise ValueError("oracle: mask_from_points failed (%d)" % rc)
+    return out
+
+
+def bilateral_filter(img, d, sigma_color, sigma_space, simd_lanes=8, tail_fma=False):
+    """cv2.bilateralFilter(img, d, sigmaColor, sigmaSpace) on a uint8 (h, w) image, OpenCV's own code path (B.1-B.6 in
+    oracle/bilateral_oracle.c; reference src/loader/loader.py:16-20,86).  simd_lanes = vector width of the OpenCV build
+    (8: AVX2 dispatch of the wheel), columns of the scalar tail take OpenCV's 4-at-a-time path."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    rc = lib().klt_oracle_bilateral_filter(img.ctypes.data, w, h, img.strides[0], int(d), float(sigma_color), float(sigma_space),
+                                           int(simd_lanes), int(bool(tail_fma)), out.ctypes.data, w)
+    if rc < 0:
+        raise ValueError("oracle: bilateral_filter failed (%d)" % rc)
     return out

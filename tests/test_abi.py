@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 def test_python_binding_covers_header(klt):
     from visual_odom_pipeline_b200 import _lib
     assert sorted(_lib.SYMBOLS) == header_symbols()
-    assert _lib.load().klt_version() == 110
+    assert _lib.load().klt_version() == 120
 
 
 def test_library_holds_sm100a_sass_only(native_lib):

@@ -68,6 +68,10 @@ SYMBOLS = {
     "klt_good_features_to_track_points_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _c.c_int,
                                                           _c.c_double, _c.c_double, _c.c_int, _P, _c.c_int, _c.POINTER(_c.c_int)]),
     "klt_corner_mask_from_points": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int64, _P]),
+    "klt_bilateral_filter": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _P, _c.c_int64, _c.c_int64, _c.c_int,
+                                        _c.c_int, _c.c_double, _c.c_double, _P]),
+    "klt_bilateral_filter_host": (_c.c_int, [_P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_double, _P,
+                                             _c.c_int64]),
 }
 
 _lib = None

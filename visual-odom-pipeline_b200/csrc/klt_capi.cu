@@ -39,6 +39,9 @@ struct klt_ctx {
     // completion counters of the one-launch pyramid build, one array per stream and geometry (klt_pyramid.cu)
     struct PyrScratch { cudaStream_t stream; unsigned* cnt; long long capacity; unsigned gen; long long key[6]; };
     std::vector<PyrScratch> pyr_scratch;
+    // weight tables of the bilateral pre-filter on the device, one per parameter set ever used (never freed before destroy)
+    struct BilateralTab { int d; double sigma_color, sigma_space; int radius, n_taps; float* d_tab; };
+    std::vector<BilateralTab> bilateral_tabs;
     // the *_host entry points share the workspaces, streams and events above: one call at a time per context
     std::mutex host_mutex;
     // pinned landing zone + helper threads for PAGEABLE host images (see stage_pageable_pair)
@@ -402,6 +405,7 @@ klt_status klt_destroy(klt_ctx* ctx)
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     cudaDeviceSynchronize();   // caller streams that used the work lists may be gone already
     for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
+    for (auto& t : ctx->bilateral_tabs) cudaFree(t.d_tab);
     delete ctx;
     return KLT_OK;
 }
@@ -1166,6 +1170,73 @@ klt_status klt_corner_mask_from_points(klt_ctx* ctx, const float* d_points, int 
     if (!ctx) return KLT_ERR_INVALID_ARG;
     KLT_DEVICE_GUARD(ctx);
     return corner_mask_from_points_launch(d_points, n, radius, w, h, d_mask, mask_pitch, (cudaStream_t)stream);
+}
+
+// ---- bilateral pre-filter (kernel in klt_bilateral.cu) -------------------------------------------
+
+static klt_status bilateral_table(klt_ctx* ctx, int d, double sigma_color, double sigma_space, int* radius, int* n_taps, const float** d_tab)
+{
+    std::lock_guard<std::mutex> guard(ctx->lk_mutex);
+    for (const auto& t : ctx->bilateral_tabs)
+        if (t.d == d && t.sigma_color == sigma_color && t.sigma_space == sigma_space) {
+            *radius = t.radius; *n_taps = t.n_taps; *d_tab = t.d_tab;
+            return KLT_OK;
+        }
+    std::vector<float> tab;
+    try { tab.resize((size_t)bilateral_table_capacity()); } catch (const std::bad_alloc&) { return KLT_ERR_OUT_OF_MEMORY; }
+    const int n = bilateral_tables(d, sigma_color, sigma_space, tab.data(), (int)tab.size());
+    if (n < 0) return KLT_ERR_UNSUPPORTED;
+    if (ctx->bilateral_tabs.size() >= 64) return KLT_ERR_UNSUPPORTED;   // parameter sets are configuration, not data
+    float* dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, (size_t)(256 + 2 * n) * sizeof(float));
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
+    e = cudaMemcpy(dev, tab.data(), (size_t)(256 + 2 * n) * sizeof(float), cudaMemcpyHostToDevice);   // synchronous: once per parameter set
+    if (e != cudaSuccess) { cudaFree(dev); return (klt_status)e; }
+    klt_ctx::BilateralTab t = {d, sigma_color, sigma_space, bilateral_radius(d, sigma_space), n, dev};
+    try { ctx->bilateral_tabs.push_back(t); } catch (const std::bad_alloc&) { cudaFree(dev); return KLT_ERR_OUT_OF_MEMORY; }
+    *radius = t.radius; *n_taps = n; *d_tab = dev;
+    return KLT_OK;
+}
+
+klt_status klt_bilateral_filter(klt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_batch_stride,
+                                uint8_t* d_dst, int64_t dst_pitch, int64_t dst_batch_stride, int batch, int d, double sigma_color,
+                                double sigma_space, void* stream)
+{
+    if (!ctx || !d_src || !d_dst || w < 1 || h < 1 || batch < 1 || src_pitch < w || dst_pitch < w) return KLT_ERR_INVALID_ARG;
+    if (d_src == d_dst) return KLT_ERR_INVALID_ARG;   // not an in-place filter (cv2 does not allow it either)
+    KLT_DEVICE_GUARD(ctx);
+    int radius = 0, n_taps = 0;
+    const float* d_tab = nullptr;
+    klt_status s = bilateral_table(ctx, d, sigma_color, sigma_space, &radius, &n_taps, &d_tab);
+    if (s != KLT_OK) return s;
+    return bilateral_launch(d_src, w, h, src_pitch, src_batch_stride, d_dst, dst_pitch, dst_batch_stride, batch, radius, n_taps, d_tab,
+                            (cudaStream_t)stream);
+}
+
+klt_status klt_bilateral_filter_host(klt_ctx* ctx, const uint8_t* img, int64_t pitch, int w, int h, int d, double sigma_color,
+                                     double sigma_space, uint8_t* out, int64_t out_pitch)
+{
+    if (!ctx || !img || !out || w < 1 || h < 1 || pitch < w || out_pitch < w) return KLT_ERR_INVALID_ARG;
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
+    int radius = 0, n_taps = 0;
+    const float* d_tab = nullptr;
+    klt_status s = bilateral_table(ctx, d, sigma_color, sigma_space, &radius, &n_taps, &d_tab);
+    if (s != KLT_OK) return s;
+    const size_t img_bytes = upload_bytes(pitch, w, h);
+    const size_t opitch = align_up((size_t)w, 128);
+    s = ensure_device_ws(ctx, img_bytes + opitch * (size_t)h);
+    if (s != KLT_OK) return s;
+    uint8_t* dws = ctx->d_ws;
+    cudaStream_t st = ctx->stream;
+    int64_t dpitch = 0;
+    s = upload_u8(dws, &dpitch, img, pitch, w, h, st);
+    if (s != KLT_OK) return s;
+    s = bilateral_launch(dws, w, h, dpitch, 0, dws + img_bytes, (long long)opitch, 0, 1, radius, n_taps, d_tab, st);
+    if (s != KLT_OK) return s;
+    KLT_CUDA(cudaMemcpy2DAsync(out, (size_t)out_pitch, dws + img_bytes, opitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
+    KLT_CUDA(cudaStreamSynchronize(st));
+    return KLT_OK;
 }
 
 }  // extern "C"

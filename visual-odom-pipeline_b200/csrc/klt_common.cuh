@@ -116,6 +116,13 @@ klt_status track_filter_launch(const float* p0, const float* p1, const float* p0
 klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaStream_t stream);
 klt_status lk_init(int device);
 
+// Bilateral pre-filter (klt_bilateral.cu)
+int bilateral_radius(int d, double sigma_space);
+int bilateral_table_capacity();
+int bilateral_tables(int d, double sigma_color, double sigma_space, float* tab, int capacity);
+klt_status bilateral_launch(const uint8_t* src, int w, int h, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
+                            long long dbatch, int batch, int radius, int n_taps, const float* d_tab, cudaStream_t stream);
+
 // Shi-Tomasi detection (klt_corners.cu)
 long long corners_ws_bytes(int w, int h, int batch);
 klt_status corner_min_eig_launch(const uint8_t* img, long long pitch, long long batch_stride, int w, int h, int batch,

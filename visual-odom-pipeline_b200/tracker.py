@@ -53,11 +53,16 @@ class DevicePyramid:
     for as long as the pyramid is used (levels 1..top would otherwise belong to another image than level 0).
     `copy=True` moves level 0 into storage owned by the pyramid (128-byte pitch: the kernels' 128-bit load path)."""
 
-    def __init__(self, images, winSize=(21, 21), maxLevel=3, ctx=None, out=None, copy=False):
+    def __init__(self, images, winSize=(21, 21), maxLevel=3, ctx=None, out=None, copy=False, prefilter=None):
         torch = _torch()
         win_w, win_h, maxLevel = _check_win_level(winSize, maxLevel)
         self.images = _as_image_batch(images)
-        if copy:
+        if prefilter is not None:
+            # the loader's bilateral filter (loader.py:16-20,86) writes the pyramid's own level 0: the raw frame is read
+            # once and no separate copy is made
+            from .filters import bilateral_filter
+            self.images = bilateral_filter(self.images, *prefilter, ctx=ctx)
+        elif copy:
             own = alloc_image_batch(self.images.shape[0], self.images.shape[1], self.images.shape[2], device=self.images.device)
             own.copy_(self.images)
             self.images = own
@@ -200,13 +205,16 @@ class KLTTracker:
     returns.
     """
 
-    def __init__(self, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03), flags=0, minEigThreshold=1e-4):
+    def __init__(self, winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.03), flags=0, minEigThreshold=1e-4, prefilter=None):
+        """prefilter = (d, sigmaColor, sigmaSpace): apply the loader's cv2.bilateralFilter (loader.py:16-20,86) to every raw
+        frame on the device while it is copied into the tracker's storage (None: frames arrive filtered)."""
         self.winSize, self.maxLevel, self.criteria = winSize, maxLevel, criteria
         self.flags, self.minEigThreshold = flags, minEigThreshold
+        self.prefilter = prefilter
         self.prev = None
 
     def reset(self, images):
-        self.prev = DevicePyramid(images, self.winSize, self.maxLevel, copy=True)
+        self.prev = DevicePyramid(images, self.winSize, self.maxLevel, copy=True, prefilter=self.prefilter)
         return self
 
     def track(self, images, prevPts, bidirectional=False):
@@ -216,7 +224,7 @@ class KLTTracker:
         started from the forward result) and returns it as a 4th output."""
         if self.prev is None:
             raise error("klt_b200: KLTTracker.track() before reset()")
-        nxt = DevicePyramid(images, self.winSize, self.maxLevel, ctx=self.prev.ctx, copy=True)
+        nxt = DevicePyramid(images, self.winSize, self.maxLevel, ctx=self.prev.ctx, copy=True, prefilter=self.prefilter)
         out = lk_track(self.prev, nxt, prevPts, None, self.criteria, self.flags, self.minEigThreshold)
         if bidirectional:
             back = lk_track(self.prev, nxt, out[0], None, self.criteria, self.flags, self.minEigThreshold)
@@ -254,9 +262,12 @@ class KLTTracker:
             survivors = p1[0][keep[0]]
             keep = keep[0]
         else:
-            self.prev = DevicePyramid(img, self.winSize, self.maxLevel, ctx=self.prev.ctx if self.prev is not None else None, copy=True)
+            self.prev = DevicePyramid(img, self.winSize, self.maxLevel, ctx=self.prev.ctx if self.prev is not None else None, copy=True,
+                                      prefilter=self.prefilter)
             survivors = torch.zeros((0, 2), dtype=torch.float32, device=img.device)
             keep = torch.zeros((0,), dtype=torch.bool, device=img.device)
+        if self.prefilter is not None:
+            img = self.prev.images            # detection runs on the filtered frame, as in the reference (loader.py:86)
         H, W = img.shape[1], img.shape[2]
         mask = D.mask_from_points(survivors, mask_radius, (H, W), ctx=self.prev.ctx)
         new = D.good_features_to_track(img, maxCorners, qualityLevel, minDistance, mask=mask.unsqueeze(0), blockSize=blockSize,
