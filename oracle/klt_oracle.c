@@ -15,7 +15,7 @@
  * Parity pinning: the reference has no tests / golden vectors for this path.
  * The oracle is therefore pinned against outputs of the reference's own implementation run
  * here -- the `cv2` module that the reference imports (4.13.0 in this image) -- in
- * tests/test_oracle_vs_cv2.py (live) and against the committed .npz vectors in tests/golden
+ * tests/test_oracle.py (live) and against the committed .npz vectors in tests/golden
  * (made by tests/golden/make_golden.py).  Target: bit-exact nextPts / status / err(status==1).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.

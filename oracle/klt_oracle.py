@@ -2,7 +2,7 @@
 
 Restates what the reference delegates to ``cv2.calcOpticalFlowPyrLK`` at
 ``src/extractor/extractor.py:44,45,65,66``.  Pinned bit-exactly against the
-live ``cv2`` module (the reference's own implementation of the path) in tests/test_oracle_vs_cv2.py
+live ``cv2`` module (the reference's own implementation of the path) in tests/test_oracle.py
 and against tests/golden/*.npz.
 """
 import ctypes

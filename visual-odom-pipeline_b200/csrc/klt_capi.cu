@@ -42,6 +42,12 @@ struct klt_ctx {
     // weight tables of the bilateral pre-filter on the device, one per parameter set ever used (never freed before destroy)
     struct BilateralTab { int d; double sigma_color, sigma_space; int radius, n_taps; float* d_tab; };
     std::vector<BilateralTab> bilateral_tabs;
+    // Pyramid reuse across host calls (the un-edited reference calls calcOpticalFlowPyrLK four times per frame on the same
+    // image pair, extractor.py:44,45,65,66): content hashes of the two uploaded images, 3 rotating slots of 4 words
+    // (call k writes slot k % 3, compares with slot (k - 1) % 3, zeroes slot (k + 1) % 3), then the skip counter
+    unsigned* d_hash = nullptr;
+    unsigned long long reuse_call = 0;
+    long long reuse_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // geometry of the last successful call (0: nothing to reuse)
     // the *_host entry points share the workspaces, streams and events above: one call at a time per context
     std::mutex host_mutex;
     // pinned landing zone + helper threads for PAGEABLE host images (see stage_pageable_pair)
@@ -86,6 +92,7 @@ struct DeviceGuard {
 klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->d_ws_bytes) return KLT_OK;
+    ctx->reuse_key[0] = 0;   // the pyramids of the last call go away with the workspace
     if (ctx->d_ws) { KLT_CUDA(cudaStreamSynchronize(ctx->stream)); KLT_CUDA(cudaStreamSynchronize(ctx->stream2)); cudaFree(ctx->d_ws); ctx->d_ws = nullptr; ctx->d_ws_bytes = 0; }
     bytes = align_up(bytes + bytes / 4, 1 << 20);
     cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
@@ -235,8 +242,10 @@ klt_status ensure_host_in(klt_ctx* ctx, size_t bytes)
 namespace {
 
 // All levels of the item range in ONE launch (pyr_build_fused_kernel); KLT_ERR_UNSUPPORTED: launch level by level.
+struct PyrReuse { const unsigned* hash_new; const unsigned* hash_old; unsigned* hash_clear; unsigned long long* skipped; unsigned mask; };
+
 klt_status pyr_build_one_launch(klt_ctx* ctx, const uint8_t* d_img, const klt_pyr_layout* lay, uint8_t* d_pyr, int first_item,
-                                int n_items, cudaStream_t stream)
+                                int n_items, cudaStream_t stream, const PyrReuse* reuse = nullptr)
 {
     const int n_steps = lay->top;
     const uint8_t* src[KLT_MAX_LEVELS];
@@ -285,6 +294,7 @@ klt_status pyr_build_one_launch(klt_ctx* ctx, const uint8_t* d_img, const klt_py
     }
     P.cnt = slot->cnt;
     P.gen = ++slot->gen;
+    if (reuse) { P.hash_new = reuse->hash_new; P.hash_old = reuse->hash_old; P.hash_clear = reuse->hash_clear; P.skipped = reuse->skipped; P.reuse_mask = reuse->mask; }
     s = pyr_fused_launch(P, stream);
     if (s != KLT_OK) --slot->gen;
     return s;
@@ -403,6 +413,7 @@ klt_status klt_destroy(klt_ctx* ctx)
     if (ctx->d_ws) cudaFree(ctx->d_ws);
     if (ctx->h_ws) cudaFreeHost(ctx->h_ws);
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
+    if (ctx->d_hash) cudaFree(ctx->d_hash);
     cudaDeviceSynchronize();   // caller streams that used the work lists may be gone already
     for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
     for (auto& t : ctx->bilateral_tabs) cudaFree(t.d_tab);
@@ -590,6 +601,31 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     if (s != KLT_OK) return s;
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream;
+    // ---- pyramid reuse across calls: the images are hashed on the device while they are re-pitched; an item whose hash
+    // equals that of the previous call (same geometry, same workspace) keeps its pyramid.  The reference's four calls per
+    // frame pass the same pair (extractor.py:44,45,65,66), so three of four builds go.  KLT_NO_PYR_REUSE=1: A/B runs.
+    static const bool no_reuse = getenv("KLT_NO_PYR_REUSE") != nullptr;
+    const bool hashing = linear && !no_reuse && lay.top >= 2;
+    const long long key[8] = {1, w, h, params->win_w, params->win_h, lay.top, (long long)ipitch, (long long)(uintptr_t)ctx->d_ws};
+    unsigned* h_new = nullptr;
+    PyrReuse reuse = {nullptr, nullptr, nullptr, nullptr, 0u};
+    if (hashing) {
+        if (!ctx->d_hash) {
+            KLT_CUDA(cudaMalloc(&ctx->d_hash, 32 * sizeof(unsigned)));
+            KLT_CUDA(cudaMemset(ctx->d_hash, 0, 32 * sizeof(unsigned)));
+            ctx->reuse_key[0] = 0;
+        }
+        const bool valid_prev = std::memcmp(key, ctx->reuse_key, sizeof(key)) == 0;
+        if (!valid_prev) KLT_CUDA(cudaMemsetAsync(ctx->d_hash, 0, 12 * sizeof(unsigned), st));   // slots may hold leftovers
+        const unsigned k = (unsigned)(ctx->reuse_call % 3);
+        h_new = ctx->d_hash + 4 * k;
+        reuse.hash_new = h_new;
+        reuse.hash_old = ctx->d_hash + 4 * ((k + 2) % 3);
+        reuse.hash_clear = ctx->d_hash + 4 * ((k + 1) % 3);
+        reuse.skipped = reinterpret_cast<unsigned long long*>(ctx->d_hash + 16);
+        reuse.mask = valid_prev ? 3u : 0u;
+    }
+    ctx->reuse_key[0] = 0;   // nothing to reuse until this call has completed
     static const bool trace = getenv("KLT_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -633,11 +669,12 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
         KLT_CUDA(cudaMemcpyAsync(d + off_raw, src_prev, raw_prev, cudaMemcpyHostToDevice, st));
         if (st2 != st) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
         if (prev_pitch == next_pitch) {
-            s = repitch_launch(d + off_raw, prev_pitch, (long long)raw_slot, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 2, st);
+            s = repitch_launch(d + off_raw, prev_pitch, (long long)raw_slot, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 2, st, h_new);
         } else {
-            s = repitch_launch(d + off_raw, prev_pitch, 0, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 1, st);
+            s = repitch_launch(d + off_raw, prev_pitch, 0, d + off_img, (long long)ipitch, (long long)ibytes, w, h, 1, st, h_new);
             if (s == KLT_OK)
-                s = repitch_launch(d + off_raw + raw_slot, next_pitch, 0, d + off_img + ibytes, (long long)ipitch, (long long)ibytes, w, h, 1, st);
+                s = repitch_launch(d + off_raw + raw_slot, next_pitch, 0, d + off_img + ibytes, (long long)ipitch, (long long)ibytes, w, h, 1, st,
+                                   h_new ? h_new + 2 : nullptr);
         }
         if (s != KLT_OK) return s;
     } else {
@@ -656,7 +693,14 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     const auto t1 = now();
     if (trace) { cudaStreamSynchronize(st); }
     const auto t1s = now();
-    s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, 0, 0, st);
+    bool reuse_armed = false;
+    if (hashing) {
+        s = pyr_build_one_launch(ctx, d + off_img, &lay, d + off_pyr, 0, 2, st, &reuse);
+        reuse_armed = (s == KLT_OK);
+        if (s == KLT_ERR_UNSUPPORTED) s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, 0, 0, st);
+    } else {
+        s = klt_pyr_build(ctx, d + off_img, &lay, d + off_pyr, 0, 0, st);
+    }
     if (s != KLT_OK) return s;
     // the pair lives in one batch-2 pyramid: prev = item 0, next = item 1
     LKLaunch L;
@@ -703,6 +747,10 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     if (trace)
         std::fprintf(stderr, "[klt trace] h2d enqueue %.1f us, h2d done +%.1f us, kernels enqueue %.1f us, kernels done +%.1f us, d2h+sync %.1f us\n",
                      us(t0, t1), us(t1, t1s), us(t1s, t2), us(t2, t2s), us(t2s, t3));
+    if (reuse_armed) {   // the pyramids in the workspace now belong to the images of this call
+        std::memcpy(ctx->reuse_key, key, sizeof(key));
+        ++ctx->reuse_call;
+    }
     std::memcpy(next_pts, ctx->h_ws, (size_t)n * 8);
     std::memcpy(err, ctx->h_ws + (size_t)n * 8, (size_t)n * 4);
     std::memcpy(status, ctx->h_ws + o_status, (size_t)n);
@@ -771,6 +819,7 @@ klt_status klt_build_optical_flow_pyramid_host(klt_ctx* ctx, const uint8_t* img,
     lay.level[0].batch_stride = (int64_t)ibytes;
     s = ensure_device_ws(ctx, ibytes + (size_t)lay.bytes);
     if (s != KLT_OK) return s;
+    ctx->reuse_key[0] = 0;   // this call overwrites the workspace of the tracking entry points
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream;
     KLT_CUDA(cudaMemcpy2DAsync(d, ipitch, img, (size_t)pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
@@ -1004,6 +1053,7 @@ klt_status klt_corner_min_eigen_val_host(klt_ctx* ctx, const uint8_t* img, int64
     const size_t ws_bytes = (size_t)corners_ws_bytes(w, h, 1);
     klt_status s = ensure_device_ws(ctx, img_bytes + eig_bytes + ws_bytes);
     if (s != KLT_OK) return s;
+    ctx->reuse_key[0] = 0;   // this call overwrites the workspace of the tracking entry points
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream;
     int64_t dpitch = 0;
@@ -1048,6 +1098,7 @@ static klt_status gftt_host_impl(klt_ctx* ctx, const uint8_t* img, int64_t pitch
     if (s != KLT_OK) return s;
     s = ensure_host_ws(ctx, 8 + direct_cap * 8);
     if (s != KLT_OK) return s;
+    ctx->reuse_key[0] = 0;   // this call overwrites the workspace of the tracking entry points
     uint8_t* d = ctx->d_ws;
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     unsigned* d_max = reinterpret_cast<unsigned*>(d + off_cnt);
@@ -1227,6 +1278,7 @@ klt_status klt_bilateral_filter_host(klt_ctx* ctx, const uint8_t* img, int64_t p
     const size_t opitch = align_up((size_t)w, 128);
     s = ensure_device_ws(ctx, img_bytes + opitch * (size_t)h);
     if (s != KLT_OK) return s;
+    ctx->reuse_key[0] = 0;   // this call overwrites the workspace of the tracking entry points
     uint8_t* dws = ctx->d_ws;
     cudaStream_t st = ctx->stream;
     int64_t dpitch = 0;
@@ -1236,6 +1288,20 @@ klt_status klt_bilateral_filter_host(klt_ctx* ctx, const uint8_t* img, int64_t p
     if (s != KLT_OK) return s;
     KLT_CUDA(cudaMemcpy2DAsync(out, (size_t)out_pitch, dws + img_bytes, opitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
     KLT_CUDA(cudaStreamSynchronize(st));
+    return KLT_OK;
+}
+
+// Diagnostics (not part of include/klt_b200.h): number of pyramids the host entry points of this context did NOT rebuild
+// because the uploaded image was unchanged.  Synchronises the context's stream.
+int klt_debug_pyr_reuse_count(klt_ctx* ctx, unsigned long long* skipped)
+{
+    if (!ctx || !skipped) return KLT_ERR_INVALID_ARG;
+    *skipped = 0;
+    if (!ctx->d_hash) return KLT_OK;
+    KLT_DEVICE_GUARD(ctx);
+    std::lock_guard<std::mutex> host_lock(ctx->host_mutex);
+    KLT_CUDA(cudaStreamSynchronize(ctx->stream));
+    KLT_CUDA(cudaMemcpy(skipped, ctx->d_hash + 16, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return KLT_OK;
 }
 

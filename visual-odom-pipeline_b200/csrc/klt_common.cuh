@@ -74,6 +74,15 @@ struct PyrFused {
     long long n_tasks;
     unsigned* cnt;      // completion counters, monotonic: a strip of launch number `gen` is complete at gen * tiles_x
     unsigned gen;
+    // Reuse of pyramids across calls of the host entry points (klt_capi.cu: track_host): item b is left as it is when
+    // bit b of reuse_mask is set and the content hash of its freshly uploaded level 0 (hash_new, 2 words per item) equals
+    // the hash of the image its levels were built from (hash_old).  hash_clear: 4 words zeroed for the call after next.
+    // skipped: statistics counter (items skipped).  All null / 0 for ordinary builds.
+    const unsigned* hash_new;
+    const unsigned* hash_old;
+    unsigned* hash_clear;
+    unsigned long long* skipped;
+    unsigned reuse_mask;
 };
 klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, uint8_t* const* dst, const int* w, const int* h,
                           const long long* spitch, const long long* sbatch, const long long* dpitch, const long long* dbatch,
@@ -87,8 +96,10 @@ klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0
 
 // Copies n_img tightly/oddly pitched u8 images (image i at src + i * sbatch, rows spitch apart, any alignment) into
 // 16-byte-aligned pitched storage.  The source buffer must be readable up to 16 bytes past the last pixel.
+// hash (optional): 2 words per image, zero on entry, receive a 64-bit content hash of the w x h pixels (position-dependent
+// mix of every 16-byte chunk, summed).
 klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
-                          long long dbatch, int w, int h, int n_img, cudaStream_t stream);
+                          long long dbatch, int w, int h, int n_img, cudaStream_t stream, unsigned* hash = nullptr);
 
 struct LKLaunch {
     PyrView prev, next;

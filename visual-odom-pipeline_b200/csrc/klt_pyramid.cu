@@ -812,6 +812,18 @@ pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
     const int b = (int)(t2 / S.strips_y);
     const int y0 = sy * S.rows;
     const int y1 = min(y0 + S.rows, S.dh);
+    if (P.hash_new != nullptr) {
+        if (task == 0 && lane == 0) { P.hash_clear[0] = 0u; P.hash_clear[1] = 0u; P.hash_clear[2] = 0u; P.hash_clear[3] = 0u; }
+        // unchanged image (same content hash as the one this item's levels were built from): leave the item alone.  All
+        // tasks of the item take the same decision; the completion counter still advances so that later launches agree.
+        if (b < 32 && ((P.reuse_mask >> b) & 1u) && P.hash_new[2 * b] == P.hash_old[2 * b] && P.hash_new[2 * b + 1] == P.hash_old[2 * b + 1]) {
+            if (lane == 0) {
+                if (l + 1 < P.n_steps) atomicAdd(P.cnt + S.cnt_off + (long long)b * S.strips_y + sy, 1u);
+                if (l == 0 && tx == 0 && sy == 0 && P.skipped) atomicAdd(P.skipped, 1ull);
+            }
+            return;
+        }
+    }
     if (l > 0) {
         const PyrStep& Q = P.s[l - 1];              // produced this step's source level
         const int s_lo = max(2 * y0 - 2, 0) / Q.rows;
@@ -879,39 +891,74 @@ klt_status launch_t(const uint8_t* src, int w, int h, long long spitch, long lon
 // Row repitch: every thread produces 16 destination bytes from 5 aligned source words (funnel shift by the
 // source row's byte misalignment).  Used by the host entry points so the H2D transfer can be ONE contiguous DMA per
 // image (a pitched 2-D copy of 1241-byte rows runs at a fraction of PCIe speed).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+template <bool HASH>
 __global__ void __launch_bounds__(256)
 repitch_kernel(const uint8_t* __restrict__ src, long long spitch, long long sbatch, uint8_t* __restrict__ dst,
-               long long dpitch, long long dbatch, int w, int chunks, int h)
+               long long dpitch, long long dbatch, int w, int chunks, int h, unsigned* __restrict__ hash)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
-    if (t >= chunks * h) return;
-    const int y = t / chunks, c = t - y * chunks;
-    const uint8_t* s = src + (long long)i * sbatch + (long long)y * spitch + 16 * c;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const int sh = (int)(a & 3) * 8;
-    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-    uint4 o;
-    o.x = __funnelshift_r(w0, w1, sh);
-    o.y = __funnelshift_r(w1, w2, sh);
-    o.z = __funnelshift_r(w2, w3, sh);
-    o.w = __funnelshift_r(w3, w4, sh);
-    *reinterpret_cast<uint4*>(dst + (long long)i * dbatch + (long long)y * dpitch + 16 * c) = o;
-    (void)w;
+    const bool live = t < chunks * h;
+    unsigned long long hv = 0ull;
+    if (live) {
+        const int y = t / chunks, c = t - y * chunks;
+        const uint8_t* s = src + (long long)i * sbatch + (long long)y * spitch + 16 * c;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, sh);
+        o.y = __funnelshift_r(w1, w2, sh);
+        o.z = __funnelshift_r(w2, w3, sh);
+        o.w = __funnelshift_r(w3, w4, sh);
+        *reinterpret_cast<uint4*>(dst + (long long)i * dbatch + (long long)y * dpitch + 16 * c) = o;
+        if constexpr (HASH) {
+            // only the w pixels of the row count: the bytes a chunk carries past column w - 1 belong to whatever lies
+            // behind the row in the landing zone
+            const int valid = min(16, w - 16 * c);
+            uint32_t q[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int nb = valid - 4 * k;
+                q[k] = nb >= 4 ? q[k] : (nb <= 0 ? 0u : (q[k] & (0xffffffffu >> (8 * (4 - nb)))));
+            }
+            const unsigned long long pos = (unsigned long long)(unsigned)t + 1ull;
+            hv = mix64((((unsigned long long)q[1] << 32) | q[0]) + pos * 0x9e3779b97f4a7c15ull) +
+                 mix64((((unsigned long long)q[3] << 32) | q[2]) ^ (pos * 0xc2b2ae3d27d4eb4full + 0x165667b19e3779f9ull));
+        }
+    }
+    if constexpr (HASH) {
+        // two independent 32-bit sums (the halves of the 64-bit terms): one REDUX each per warp, one atomic each
+        const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(hv & 0xffffffffull));
+        const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(hv >> 32));
+        if ((threadIdx.x & 31) == 0 && (lo | hi)) {
+            atomicAdd(hash + 2 * i, lo);
+            atomicAdd(hash + 2 * i + 1, hi);
+        }
+    }
 }
 
 }  // namespace
 
 klt_status repitch_launch(const uint8_t* src, long long spitch, long long sbatch, uint8_t* dst, long long dpitch,
-                          long long dbatch, int w, int h, int n_img, cudaStream_t stream)
+                          long long dbatch, int w, int h, int n_img, cudaStream_t stream, unsigned* hash)
 {
     if (!src || !dst || w <= 0 || h <= 0 || n_img <= 0 || n_img > 65535) return KLT_ERR_INVALID_ARG;
     if ((((uintptr_t)dst | (uintptr_t)dpitch | (uintptr_t)dbatch) & 15) != 0 || dpitch < (w + 15) / 16 * 16) return KLT_ERR_INVALID_ARG;
     const int chunks = (w + 15) / 16;
     if ((long long)chunks * h > 0x7fffff00LL) return KLT_ERR_UNSUPPORTED;
     dim3 grid((unsigned)(((long long)chunks * h + 255) / 256), n_img, 1);
-    repitch_kernel<<<grid, 256, 0, stream>>>(src, spitch, sbatch, dst, dpitch, dbatch, w, chunks, h);
+    if (hash) repitch_kernel<true><<<grid, 256, 0, stream>>>(src, spitch, sbatch, dst, dpitch, dbatch, w, chunks, h, hash);
+    else repitch_kernel<false><<<grid, 256, 0, stream>>>(src, spitch, sbatch, dst, dpitch, dbatch, w, chunks, h, nullptr);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
@@ -1070,6 +1117,7 @@ klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, u
         if (counters > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
     }
     P.n_steps = n_steps; P.batch = batch; P.n_tasks = tasks;
+    P.hash_new = nullptr; P.hash_old = nullptr; P.hash_clear = nullptr; P.skipped = nullptr; P.reuse_mask = 0u;
     *n_counters = counters;
     return KLT_OK;
 }
