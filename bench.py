@@ -374,7 +374,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    host_cores = sharding.bind_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    host_cores = [] if os.environ.get("KLT_NO_BIND") else sharding.bind_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dev = torch.device("cuda", local_rank)
     ctx = K.default_context(local_rank)
     L = _lib.load()
