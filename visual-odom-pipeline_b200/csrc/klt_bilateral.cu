@@ -40,7 +40,10 @@ bilateral_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch
     for (int i = tid; i < 256 + 2 * n_taps; i += kBX * kBY) {
         if (i < 256) s_color[i] = tab[i];
         else if (i < 256 + n_taps) s_space[i - 256] = tab[i];
-        else s_ofs[i - 256 - n_taps] = __float_as_int(tab[i]);
+        else {
+            const int o = __float_as_int(tab[i]);                       // dy << 16 | (dx & 0xffff)
+            s_ofs[i - 256 - n_taps] = (o >> 16) * tp + (int)(short)(o & 0xffff);   // byte offset inside the tile
+        }
     }
     const uint8_t* __restrict__ img = src + (long long)blockIdx.z * sbatch;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
@@ -62,8 +65,7 @@ bilateral_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch
         float sum = 0.f, wsum = 0.f;
         if (x < x_tail) {
             for (int k = 0; k < n_taps; ++k) {
-                const int o = s_ofs[k];
-                const int v = c0[(o >> 16) * tp + (int)(short)(o & 0xffff)];
+                const int v = c0[s_ofs[k]];
                 const float wt = __fmul_rn(s_space[k], s_color[abs(v - v0)]);
                 wsum = __fadd_rn(wsum, wt);
                 sum = __fmaf_rn((float)v, wt, sum);
@@ -76,8 +78,7 @@ bilateral_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch
                 float wt[4], p[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int o = s_ofs[k + q];
-                    const int v = c0[(o >> 16) * tp + (int)(short)(o & 0xffff)];
+                    const int v = c0[s_ofs[k + q]];
                     wt[q] = __fmul_rn(s_space[k + q], s_color[abs(v - v0)]);
                     p[q] = __fmul_rn((float)v, wt[q]);
                 }
@@ -85,8 +86,7 @@ bilateral_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch
                 sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(p[0], p[2]), __fadd_rn(p[1], p[3])));
             }
             for (; k < n_taps; ++k) {
-                const int o = s_ofs[k];
-                const int v = c0[(o >> 16) * tp + (int)(short)(o & 0xffff)];
+                const int v = c0[s_ofs[k]];
                 const float wt = __fmul_rn(s_space[k], s_color[abs(v - v0)]);
                 wsum = __fadd_rn(wsum, wt);
                 sum = __fadd_rn(sum, __fmul_rn((float)v, wt));

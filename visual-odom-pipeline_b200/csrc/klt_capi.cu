@@ -1276,18 +1276,46 @@ klt_status klt_bilateral_filter_host(klt_ctx* ctx, const uint8_t* img, int64_t p
     if (s != KLT_OK) return s;
     const size_t img_bytes = upload_bytes(pitch, w, h);
     const size_t opitch = align_up((size_t)w, 128);
-    s = ensure_device_ws(ctx, img_bytes + opitch * (size_t)h);
+    const size_t out_bytes = opitch * (size_t)h;
+    s = ensure_device_ws(ctx, img_bytes + out_bytes);
+    if (s != KLT_OK) return s;
+    s = ensure_host_ws(ctx, out_bytes);
     if (s != KLT_OK) return s;
     ctx->reuse_key[0] = 0;   // this call overwrites the workspace of the tracking entry points
     uint8_t* dws = ctx->d_ws;
     cudaStream_t st = ctx->stream;
+    // Pageable input (what cv2.imread returns): staged through the pinned landing zone by the calling thread and the
+    // helper threads, like the images of the tracking entry point.  The result lands in the pinned staging buffer with
+    // one contiguous DMA and is copied out row by row by the CPU (a D2H copy into pageable memory is staged by the
+    // driver, synchronously and slowly).
+    const size_t raw = (size_t)(h - 1) * (size_t)pitch + (size_t)w;
+    const uint8_t* src = img;
+    if (raw <= 2 * (size_t)w * (size_t)h && raw >= (128u << 10) && is_pageable(img)) {
+        s = ensure_host_in(ctx, align_up(raw, 256));
+        if (s != KLT_OK) return s;
+        if (!ctx->stager) {
+            ctx->stager = new (std::nothrow) klt_ctx::Stager();
+            if (ctx->stager && !ctx->stager->start()) { delete ctx->stager; ctx->stager = nullptr; }
+        }
+        if (ctx->stager) {
+            ctx->stager->post(img, ctx->h_in, raw, nullptr, nullptr, 0);
+            ctx->stager->finish_job(0);
+            ctx->stager->finish_job(1);
+            src = ctx->h_in;
+        }
+    }
     int64_t dpitch = 0;
-    s = upload_u8(dws, &dpitch, img, pitch, w, h, st);
+    s = upload_u8(dws, &dpitch, src, pitch, w, h, st);
     if (s != KLT_OK) return s;
     s = bilateral_launch(dws, w, h, dpitch, 0, dws + img_bytes, (long long)opitch, 0, 1, radius, n_taps, d_tab, st);
     if (s != KLT_OK) return s;
-    KLT_CUDA(cudaMemcpy2DAsync(out, (size_t)out_pitch, dws + img_bytes, opitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
+    KLT_CUDA(cudaMemcpyAsync(ctx->h_ws, dws + img_bytes, out_bytes, cudaMemcpyDeviceToHost, st));
     KLT_CUDA(cudaStreamSynchronize(st));
+    if ((size_t)out_pitch == (size_t)w && opitch == (size_t)w) {
+        std::memcpy(out, ctx->h_ws, out_bytes);
+    } else {
+        for (int y = 0; y < h; ++y) std::memcpy(out + (size_t)y * (size_t)out_pitch, ctx->h_ws + (size_t)y * opitch, (size_t)w);
+    }
     return KLT_OK;
 }
 
