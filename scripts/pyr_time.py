@@ -21,11 +21,16 @@ def run(h, w, B, win=(21, 21), max_level=3, reps=20):
         assert L.klt_pyr_down(pyr.ctx.handle, imgs.data_ptr(), w, h, imgs.stride(1), imgs.stride(0), pyr.buffer.data_ptr() + l1.offset,
                               l1.pitch, l1.batch_stride, B, st) == 0
     for _ in range(3): down(); pyr.build()
-    t1, t2 = [], []
+    # all repetitions are queued back to back and synchronised once: an event recorded on an idle stream would also time
+    # the CPU's launch path (~5 us through ctypes), which is not kernel time
+    evs = []
     for _ in range(reps):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        e[0].record(); down(); e[1].record(); pyr.build(); e[2].record(); torch.cuda.synchronize()
-        t1.append(e[0].elapsed_time(e[1])); t2.append(e[1].elapsed_time(e[2]))
+        e[0].record(); down(); e[1].record(); pyr.build(); e[2].record()
+        evs.append(e)
+    torch.cuda.synchronize()
+    t1 = [e[0].elapsed_time(e[1]) for e in evs]
+    t2 = [e[1].elapsed_time(e[2]) for e in evs]
     b01 = B * (w * h + ((w + 1) // 2) * ((h + 1) // 2)); ball = pyr.algorithmic_bytes()
     m1, m2 = statistics.median(t1), statistics.median(t2)
     ok = True
