@@ -622,6 +622,27 @@ def main():
         batched = {"pairs": P, "points": P * n, "ms": bms, "keypoints_per_sec": P * n / (bms * 1e-3), "pairs_per_sec": P / (bms * 1e-3),
                    "int32_mac_frac": (mac_pt * P * n / (bms * 1e-3) / 1e9) / mac_peak}
 
+        # ---- the generic kernel (any window other than 21x21 / 31x31): same pool, winSize 15x15 and 25x17 -----------------------
+        generic = []
+        for gwin in ((15, 15), (25, 17)):
+            gparams = make_params(gwin, wl["criteria"], 0, 1e-4)
+            ge = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            gpairs = min(P, 32)
+            gq = torch.empty((gpairs, n, 2), dtype=torch.float32, device=dev)      # own outputs: the pool's are checked below
+            gs = torch.empty((gpairs, n), dtype=torch.uint8, device=dev)
+            gerr = torch.empty((gpairs, n), dtype=torch.float32, device=dev)
+            for r in range(3):
+                if r == 2:
+                    ge[0].record(stream)
+                rc = L.klt_lk_track(h_ctx, img0, pyr0, img0, pyr0, layB_ref, 0, 1, 2, gpairs, pts0, gq.data_ptr(), gs.data_ptr(), gerr.data_ptr(),
+                                    None, n, ctypes.byref(gparams), sptr)
+                assert rc == 0, _lib.status_string(rc)
+            ge[1].record(stream)
+            torch.cuda.synchronize()
+            gms = ge[0].elapsed_time(ge[1])
+            generic.append({"winSize": list(gwin), "pairs": gpairs, "points": gpairs * n, "ms": gms, "keypoints_per_sec": gpairs * n / (gms * 1e-3),
+                            "kernel": "lk_kernel (klt_lk.cu: one warp per keypoint, runtime window geometry)"})
+
         detection = prefilter = None
         if not args.no_detection and h > 31 and w > 31:
             detection = run_detection(args, wl, K, L, hp, hpin, imgs, P, n_host, local_rank, world, dev, stream)
@@ -688,6 +709,7 @@ def main():
             "lk_roofline": lk_roofline,
             "pipelined": pipelined,
             "batched_lk": batched,
+            "generic_lk": generic,
             "sharded_batch": sharded,
             "parity": parity,
             "detection": detection,
