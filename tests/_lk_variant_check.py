@@ -18,6 +18,8 @@ CASES = [
     (480, 640, 500, (21, 21), 3, (3, 10, 0.01), S.BENIGN, 10, {}),
     (120, 160, 96, (21, 21), 3, (3, 30, 0.01), S.BENIGN, 5, {}),
 ]
+# windows larger than a white-noise image: the gradient energy of a window sits in one or two threads (clamp regression)
+NOISE_CASES = [(12, 12, (21, 21)), (12, 12, (31, 31)), (25, 25, (31, 31))]
 bad = 0
 for rep in range(2):
     for h, w, n, win, lvl, crit, motion, margin, kw in CASES:
@@ -31,5 +33,15 @@ for rep in range(2):
         if not ok:
             bad += 1
             print("MISMATCH", (h, w, n, win, crit), "points differing:", int((q.view(np.uint32) != rq.view(np.uint32)).any(-1).sum()))
+rng = np.random.default_rng(0)
+for h, w, win in NOISE_CASES:
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    b = np.roll(a, (0, 1), axis=(0, 1))
+    p = np.stack([rng.uniform(-8, w + 8, 200), rng.uniform(-8, h + 8, 200)], -1).astype(np.float32).reshape(-1, 1, 2)
+    q, st, er = K.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=0, criteria=(3, 30, 0.01))
+    rq, rs, re_ = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=0, criteria=(3, 30, 0.01))
+    if not (np.array_equal(q.view(np.uint32), rq.view(np.uint32)) and np.array_equal(st, rs)):
+        bad += 1
+        print("MISMATCH noise", (h, w, win), "points differing:", int((q.view(np.uint32) != rq.view(np.uint32)).any(-1).sum()))
 print("variant", {k: v for k, v in os.environ.items() if k.startswith("KLT_LK")}, "bad cases:", bad)
 sys.exit(1 if bad else 0)

@@ -524,3 +524,19 @@ def test_pyramid_reuse_across_calls_detects_changed_images(klt, cv2):
     got = klt.trackBidirectional(b, c, p, 30, **lk)
     assert_lk_equal((got[0], got[3], got[4]), cv2.calcOpticalFlowPyrLK(b, c, p, None, **lk), "bidirectional")
     assert skipped() == s0 + 12
+
+
+def test_lk_windows_larger_than_the_image(klt, cv2):
+    """Regression (found by tests/test_gpu_random.py): on a 12 x 12 white-noise image with a 21 x 21 window almost the whole
+    gradient energy of a window sits in one or two threads of the team; the per-thread clamp of the exactness bounds used to
+    be 2^25 / WPP, so for the 4-warp team a clamped thread no longer proved "not exact" and one float32 sum was taken from the
+    integer total although OpenCV's partial sums round."""
+    rng = np.random.default_rng(0)
+    for (h, w, win) in [(12, 12, (21, 21)), (12, 12, (31, 31)), (9, 40, (21, 21)), (25, 25, (31, 31))]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        b = np.roll(a, (0, 1), axis=(0, 1))
+        p = np.stack([rng.uniform(-8, w + 8, 200), rng.uniform(-8, h + 8, 200)], -1).astype(np.float32).reshape(-1, 1, 2)
+        for lvl in (0, 2):
+            ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=(3, 30, 0.01))
+            assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=(3, 30, 0.01)), ref,
+                            "%dx%d win %s level %d" % (w, h, win, lvl))

@@ -97,8 +97,10 @@ klt_status ensure_device_ws(klt_ctx* ctx, size_t bytes)
     bytes = align_up(bytes + bytes / 4, 1 << 20);
     cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
-    // padding columns / rows of the workspace are read (never used) by the 16-byte granule copies: define them once
-    if (cudaMemset(ctx->d_ws, 0, bytes) != cudaSuccess) cudaGetLastError();
+    // padding columns / rows of the workspace are read (never used) by the 16-byte granule copies: define them once.
+    // The memset runs on the legacy stream, which the context's non-blocking streams do not wait for: synchronise, or it
+    // could wipe what the current call is about to upload (seen once as a flaky detection result).
+    if (cudaMemset(ctx->d_ws, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
     ctx->d_ws_bytes = bytes;
     return KLT_OK;
 }
@@ -613,6 +615,7 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
         if (!ctx->d_hash) {
             KLT_CUDA(cudaMalloc(&ctx->d_hash, 32 * sizeof(unsigned)));
             KLT_CUDA(cudaMemset(ctx->d_hash, 0, 32 * sizeof(unsigned)));
+            KLT_CUDA(cudaDeviceSynchronize());   // the memset is not ordered with the context's non-blocking streams
             ctx->reuse_key[0] = 0;
         }
         const bool valid_prev = std::memcmp(key, ctx->reuse_key, sizeof(key)) == 0;
@@ -661,11 +664,17 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
                 staged = true;
             }
         }
-        if (staged) ctx->stager->finish_job(0);
+        // (an error return between the two halves must not leave helpers reading the caller's buffers)
+        struct StageGuard {
+            klt_ctx::Stager* s; bool done0 = false, done1 = false;
+            void finish(int job) { if (s && !(job ? done1 : done0)) { s->finish_job(job); (job ? done1 : done0) = true; } }
+            ~StageGuard() { finish(0); finish(1); }
+        } stage_guard{staged ? ctx->stager : nullptr};
+        stage_guard.finish(0);
         KLT_CUDA(cudaMemcpyAsync(d + off_raw + raw_slot, src_next, raw_next, cudaMemcpyHostToDevice, st2));
         if (st2 != st) KLT_CUDA(cudaEventRecord(ctx->ev2, st2));
         KLT_CUDA(cudaMemcpyAsync(d + off_pts, src_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        if (staged) ctx->stager->finish_job(1);
+        stage_guard.finish(1);
         KLT_CUDA(cudaMemcpyAsync(d + off_raw, src_prev, raw_prev, cudaMemcpyHostToDevice, st));
         if (st2 != st) KLT_CUDA(cudaStreamWaitEvent(st, ctx->ev2, 0));
         if (prev_pitch == next_pitch) {
@@ -1241,7 +1250,8 @@ static klt_status bilateral_table(klt_ctx* ctx, int d, double sigma_color, doubl
     float* dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, (size_t)(256 + 2 * n) * sizeof(float));
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
-    e = cudaMemcpy(dev, tab.data(), (size_t)(256 + 2 * n) * sizeof(float), cudaMemcpyHostToDevice);   // synchronous: once per parameter set
+    e = cudaMemcpy(dev, tab.data(), (size_t)(256 + 2 * n) * sizeof(float), cudaMemcpyHostToDevice);   // once per parameter set
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // (a pageable H2D copy may return before its DMA has landed)
     if (e != cudaSuccess) { cudaFree(dev); return (klt_status)e; }
     klt_ctx::BilateralTab t = {d, sigma_color, sigma_space, bilateral_radius(d, sigma_space), n, dev};
     try { ctx->bilateral_tabs.push_back(t); } catch (const std::bad_alloc&) { cudaFree(dev); return KLT_ERR_OUT_OF_MEMORY; }

@@ -537,7 +537,10 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             }
         }
         {
-            const unsigned cap = (1u << 25) / WPP;  // keeps the point-wide totals below 2^31
+            // A clamped value must still prove "not exact": the clamp is kExact + 1 whatever the team size (a smaller one
+            // -- round 1 used 2^25 / WPP -- let a window whose whole gradient energy sits in one thread pass the test:
+            // found by tests/test_gpu_random.py on a 12 x 12 image).  Totals stay below 2^32: compared as unsigned.
+            const unsigned cap = (unsigned)kExact + 1u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 vals[j] = (int)min(q11[j], cap);
@@ -674,10 +677,11 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             float b1 = 0.f, b2 = 0.f;
             bool classes = sticky;
             if (!sticky) {
-                // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamp so the point total cannot wrap
-                bnd = min(bnd, (1 << 25) / WPP);
+                // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamped to kExact + 1 so that the point total
+                // (<= 128 * (2^24 + 1) < 2^32, compared as unsigned) cannot wrap and a clamped thread alone fails the test
+                bnd = min(bnd, kExact + 1);
                 point_sum3<WPP>(s1, s2, bnd, red3, par3, wip, lane, bar);
-                if (bnd <= kExact) {
+                if ((unsigned)bnd <= (unsigned)kExact) {
                     // every float32 partial sum OpenCV forms (lanes, tail, final combine) is an exact integer
                     b1 = __fmul_rn((float)s1, 9.5367431640625e-07f);
                     b2 = __fmul_rn((float)s2, 9.5367431640625e-07f);
@@ -714,7 +718,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     cv[14] += tail ? (ub[0] + ub[1] + ub[2] + ub[3]) : 0;
                 }
 #pragma unroll
-                for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (1 << 22) / WPP);
+                for (int i = 10; i < 15; ++i) cv[i] = min(cv[i], (kExact >> 4) + 1);   // clamped => not exact (see the G sums)
                 const int ctot = point_sum15_lane<WPP>(cv, red16, par16, wip, lane, bar);
                 const bool is_bound = (lane >= 10) && (lane < 15);
                 const bool exact = __all_sync(kFull, !is_bound || ctot <= (kExact >> 4));
