@@ -9,11 +9,11 @@ from conftest import assert_lk_equal
 from test_random_cpu import _image
 
 pytestmark = pytest.mark.gpu
-SETTINGS = dict(max_examples=60, deadline=None, derandomize=True)
+SETTINGS = dict(max_examples=250, deadline=None, derandomize=True)
 
 
 @settings(**SETTINGS)
-@given(h=st.integers(12, 200), w=st.integers(12, 260), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 2),
+@given(h=st.integers(12, 200), w=st.integers(12, 260), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 4),
        win=st.one_of(st.sampled_from([(21, 21), (31, 31)]), st.tuples(st.integers(3, 41), st.integers(3, 41))),
        max_level=st.integers(0, 5), n=st.integers(1, 300),
        crit=st.sampled_from([(3, 30, 0.01), (3, 30, 0.03), (3, 5, 0.03), (1, 7, 0.0), (2, 0, 0.05), (3, 100, 1e-4)]),
@@ -43,8 +43,8 @@ def test_pyramid_equals_cv2_on_random_shapes(klt, h, w, seed, levels):
         assert np.array_equal(got[l], ref), (h, w, l)
 
 
-@settings(max_examples=30, deadline=None, derandomize=True)
-@given(h=st.integers(40, 160), w=st.integers(40, 220), seed=st.integers(0, 10 ** 6), kind=st.integers(1, 2),
+@settings(max_examples=80, deadline=None, derandomize=True)
+@given(h=st.integers(40, 160), w=st.integers(40, 220), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 4),
        block=st.sampled_from([3, 5, 15, 31]), max_corners=st.sampled_from([0, 10, 1000]), q=st.sampled_from([0.01, 0.03, 0.2]),
        min_dist=st.sampled_from([0.0, 1.0, 7.5, 10.0]), masked=st.booleans())
 def test_good_features_equals_cv2_on_random_inputs(klt, h, w, seed, kind, block, max_corners, q, min_dist, masked):
@@ -61,8 +61,8 @@ def test_good_features_equals_cv2_on_random_inputs(klt, h, w, seed, kind, block,
         assert got.shape == ref.shape and np.array_equal(got, ref), (h, w, block, max_corners, q, min_dist)
 
 
-@settings(max_examples=30, deadline=None, derandomize=True)
-@given(h=st.integers(5, 150), w=st.integers(5, 260), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 2),
+@settings(max_examples=80, deadline=None, derandomize=True)
+@given(h=st.integers(5, 150), w=st.integers(5, 260), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 4),
        params=st.sampled_from([(5, 1.5, 1.5), (3, 12.0, 1.0), (9, 30.0, 4.0), (0, 5.0, 1.1)]))
 def test_bilateral_equals_the_oracle_on_random_inputs(klt, oracle, h, w, seed, kind, params):
     a = _image(h, w, seed, kind)

@@ -6,7 +6,7 @@ from hypothesis import given, settings, strategies as st
 
 from conftest import assert_lk_equal
 
-SETTINGS = dict(max_examples=40, deadline=None, derandomize=True)
+SETTINGS = dict(max_examples=80, deadline=None, derandomize=True)
 
 
 def _image(h, w, seed, kind):
@@ -14,6 +14,13 @@ def _image(h, w, seed, kind):
     if kind == 0:       # white noise
         return rng.integers(0, 256, (h, w), dtype=np.uint8)
     yy, xx = np.mgrid[0:h, 0:w]
+    if kind == 3:       # checkerboards of 0 / 255 with cells of 1..4 pixels: the largest gradients the arithmetic can see
+        c = 1 + seed % 4
+        return ((((xx // c) + (yy // c)) % 2) * 255).astype(np.uint8)
+    if kind == 4:       # constant image (zero gradients: the min-eigenvalue gate) with one bright pixel
+        img = np.full((h, w), seed % 256, np.uint8)
+        img[(seed // 7) % h, (seed // 3) % w] = 255 - seed % 256
+        return img
     if kind == 1:       # smooth blobs + noise
         img = 128 + 70 * np.sin(xx / 5.0 + seed) * np.cos(yy / 7.0) + rng.normal(0, 6, (h, w))
     else:               # steps and flat areas
@@ -22,7 +29,7 @@ def _image(h, w, seed, kind):
 
 
 @settings(**SETTINGS)
-@given(h=st.integers(12, 90), w=st.integers(12, 130), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 2),
+@given(h=st.integers(12, 90), w=st.integers(12, 130), seed=st.integers(0, 10 ** 6), kind=st.integers(0, 4),
        win_w=st.integers(3, 25), win_h=st.integers(3, 25), max_level=st.integers(0, 4), n=st.integers(1, 60),
        crit=st.sampled_from([(3, 30, 0.01), (3, 5, 0.03), (1, 7, 0.0), (2, 0, 0.05), (3, 100, 1e-4)]),
        flags=st.sampled_from([0, 8]), shift=st.tuples(st.integers(-4, 4), st.integers(-4, 4)))
