@@ -47,6 +47,8 @@ struct klt_ctx {
     // (call k writes slot k % 3, compares with slot (k - 1) % 3, zeroes slot (k + 1) % 3), then the skip counter
     unsigned* d_hash = nullptr;
     unsigned long long reuse_call = 0;
+    const void* last_imgs[2] = {nullptr, nullptr};        // host addresses of the last call's images: a repeat is likely only
+    long long last_pitch[2] = {0, 0};                     // when the caller passes the same arrays again
     long long reuse_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // geometry of the last successful call (0: nothing to reuse)
     // the *_host entry points share the workspaces, streams and events above: one call at a time per context
     std::mutex host_mutex;
@@ -607,7 +609,12 @@ klt_status track_host(klt_ctx* ctx, const uint8_t* prev_img, int64_t prev_pitch,
     // equals that of the previous call (same geometry, same workspace) keeps its pyramid.  The reference's four calls per
     // frame pass the same pair (extractor.py:44,45,65,66), so three of four builds go.  KLT_NO_PYR_REUSE=1: A/B runs.
     static const bool no_reuse = getenv("KLT_NO_PYR_REUSE") != nullptr;
-    const bool hashing = linear && !no_reuse && lay.top >= 2;
+    // Hashing costs 2.4 us per call, a skipped build saves 7: it is switched on only while the caller keeps passing the same
+    // two arrays (the first repeat builds and records the hashes, the following ones skip)
+    const bool same_arrays = ctx->last_imgs[0] == prev_img && ctx->last_imgs[1] == next_img && ctx->last_pitch[0] == prev_pitch &&
+                             ctx->last_pitch[1] == next_pitch;
+    ctx->last_imgs[0] = prev_img; ctx->last_imgs[1] = next_img; ctx->last_pitch[0] = prev_pitch; ctx->last_pitch[1] = next_pitch;
+    const bool hashing = linear && !no_reuse && lay.top >= 2 && same_arrays;
     const long long key[8] = {1, w, h, params->win_w, params->win_h, lay.top, (long long)ipitch, (long long)(uintptr_t)ctx->d_ws};
     unsigned* h_new = nullptr;
     PyrReuse reuse = {nullptr, nullptr, nullptr, nullptr, 0u};
