@@ -218,12 +218,24 @@ struct klt_ctx::Stager {
 
 namespace {
 
+// Is this host address ordinary (pageable) memory?  cudaPointerGetAttributes costs about a microsecond, and callers pass
+// the same few buffers again and again: the answer is remembered per 4 KB page in a small direct-mapped table.  A stale
+// entry (the page was freed and came back as the other kind of memory) only costs speed: a pinned buffer gets staged, or
+// a pageable one is handed to the driver's own staging.
 bool is_pageable(const void* p)
 {
+    struct Entry { uintptr_t page; bool pageable; };
+    thread_local Entry cache[64] = {};
+    const uintptr_t page = reinterpret_cast<uintptr_t>(p) >> 12;
+    Entry& e = cache[(page ^ (page >> 6)) & 63];
+    if (e.page == page && page != 0) return e.pageable;
     cudaPointerAttributes a;
-    const cudaError_t e = cudaPointerGetAttributes(&a, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return true; }
-    return a.type == cudaMemoryTypeUnregistered;
+    const cudaError_t err = cudaPointerGetAttributes(&a, p);
+    bool pageable = true;
+    if (err != cudaSuccess) cudaGetLastError();
+    else pageable = (a.type == cudaMemoryTypeUnregistered);
+    e.page = page; e.pageable = pageable;
+    return pageable;
 }
 
 klt_status ensure_host_in(klt_ctx* ctx, size_t bytes)
