@@ -23,10 +23,6 @@
 //    only; interior lanes never branch on coordinates.
 #include "klt_common.cuh"
 
-#ifndef KLT_PYR_MINB
-#define KLT_PYR_MINB 3   // resident CTAs per SM the ring kernels are compiled for (80 registers); 4 measured in DESIGN.md
-#endif
-
 #include <cuda.h>
 #include <cstdlib>
 #include <type_traits>
@@ -727,7 +723,7 @@ klt_status launch_tma(const uint8_t* src, int w, int h, long long spitch, long l
     const int tiles_x = n8 + (rem > 0);
     // Strip height: a warp task costs about (2*rows + 3 input rows + pipeline fill); tasks run in rounds of `resident`
     // warps (3 CTAs of 8 warps per SM).  Pick the height that minimises rounds x task cost.
-    const long long resident = (long long)sm_count * KLT_PYR_MINB * kWarpsPerBlock;
+    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
     int rows = 2;
     double best = 1e300;
     for (int r = 2; r <= 48; ++r) {
@@ -1089,7 +1085,7 @@ klt_status pyr_down_launch(const uint8_t* src, int w, int h, long long spitch, l
         // TMA kernel for A/B runs only.
         static const char* force_tma = getenv("KLT_PYR_TMA");
         if (force_tma && force_tma[0] == '1') return launch_tma(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
-        return launch_ring<KLT_PYR_MINB>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
+        return launch_ring<3>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream);
     }
     if (aligned) {
         return use8 ? launch_t<8, true>(src, w, h, spitch, sbatch, dst, dw, dh, dpitch, dbatch, batch, sm_count, stream)
@@ -1107,7 +1103,7 @@ klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, u
 {
     if (n_steps < 1 || n_steps > KLT_MAX_LEVELS - 1 || batch <= 0) return KLT_ERR_UNSUPPORTED;
     using RC = RingCfg<8>;
-    const long long resident = (long long)sm_count * KLT_PYR_MINB * kWarpsPerBlock;
+    const long long resident = (long long)sm_count * 3 * kWarpsPerBlock;
     long long tasks = 0, counters = 0;
     for (int i = 0; i < n_steps; ++i) {
         PyrStep& S = P.s[i];
@@ -1141,12 +1137,12 @@ klt_status pyr_fused_launch(const PyrFused& P, cudaStream_t stream)
     static PerDeviceOnce configured;
     const int smem = RC::WARP_BYTES * kWarpsPerBlock;
     if (configured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_build_fused_kernel<KLT_PYR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pyr_build_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
     }
     const long long blocks = (P.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_build_fused_kernel<KLT_PYR_MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
+    pyr_build_fused_kernel<3><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
