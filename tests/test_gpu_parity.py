@@ -547,3 +547,39 @@ def test_lk_windows_larger_than_the_image(klt, cv2):
             ref = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=(3, 30, 0.01))
             assert_lk_equal(klt.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=lvl, criteria=(3, 30, 0.01)), ref,
                             "%dx%d win %s level %d" % (w, h, win, lvl))
+
+
+def test_pyramid_and_lk_replay_from_a_cuda_graph(klt, cv2, torch_cuda):
+    """The device-pointer entry points are plain launches once their scratch exists (the one-launch pyramid build keeps its
+    launch counter on the device), so a frame's work -- both pyramids + LK -- can be captured once and replayed from a CUDA
+    graph with new frame contents in the same buffers."""
+    torch = torch_cuda
+    from visual_odom_pipeline_b200 import tracker as T
+    h, w, win, crit = 240, 320, (21, 21), (3, 30, 0.01)
+    frames = S.sequence(h, w, 5, seed=12)
+    a, b = T.alloc_image_batch(1, h, w), T.alloc_image_batch(1, h, w)
+    a[0].copy_(torch.from_numpy(frames[0])); b[0].copy_(torch.from_numpy(frames[1]))
+    pts = torch.from_numpy(S.uniform_points(300, h, w, seed=2).reshape(1, -1, 2)).cuda()
+    P0, P1 = T.DevicePyramid(a, win, 3), T.DevicePyramid(b, win, 3)
+    assert P0.top >= 2                                   # the one-launch build is the path under test
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                        # warm-up on the capture stream: scratch is allocated per stream
+        for _ in range(2):
+            P0.build(); P1.build()
+            T.lk_track(P0, P1, pts, criteria=crit)
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        P0.build(); P1.build()
+        q, st, er = T.lk_track(P0, P1, pts, criteria=crit)
+    for t in range(1, len(frames)):
+        a[0].copy_(torch.from_numpy(frames[t - 1])); b[0].copy_(torch.from_numpy(frames[t]))
+        p_h = S.uniform_points(300, h, w, seed=20 + t)
+        pts.copy_(torch.from_numpy(p_h.reshape(1, -1, 2)))
+        torch.cuda.synchronize()
+        for _ in range(2):                               # replayed twice: the counters of the pyramid build keep advancing
+            g.replay()
+        torch.cuda.synchronize()
+        ref = cv2.calcOpticalFlowPyrLK(frames[t - 1], frames[t], p_h, None, winSize=win, maxLevel=3, criteria=crit)
+        assert_lk_equal((q.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy()), ref, "replay %d" % t)

@@ -37,7 +37,7 @@ struct klt_ctx {
     size_t h_ws_bytes = 0;
     std::mutex lk_mutex;
     // completion counters of the one-launch pyramid build, one array per stream and geometry (klt_pyramid.cu)
-    struct PyrScratch { cudaStream_t stream; unsigned* cnt; long long capacity; unsigned gen; long long key[6]; };
+    struct PyrScratch { cudaStream_t stream; unsigned* cnt; unsigned* cnt_dev; long long capacity; unsigned gen; long long key[6]; };
     std::vector<PyrScratch> pyr_scratch;
     // weight tables of the bilateral pre-filter on the device, one per parameter set ever used (never freed before destroy)
     struct BilateralTab { int d; double sigma_color, sigma_space; int radius, n_taps; float* d_tab; };
@@ -279,40 +279,51 @@ klt_status pyr_build_one_launch(klt_ctx* ctx, const uint8_t* d_img, const klt_py
     long long n_cnt = 0;
     klt_status s = pyr_fused_plan(P, n_steps, src, dst, w, h, sp, sb, dp, db, n_items, ctx->sm_count, &n_cnt);
     if (s != KLT_OK) return s;
+    // A launch that is being recorded into a CUDA graph must not depend on host-side state (the launch number): it takes
+    // the device-side form of the kernel, on a counter array of its own (allocated together with the ordinary one, so a
+    // build that ran once on this stream before the capture has prepared it).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    const bool device_gen = cap != cudaStreamCaptureStatusNone;
     // the counter layout depends on the geometry only (not on which items are built): one array per stream and geometry
     const long long key[6] = {lay->level[0].w, lay->level[0].h, n_steps, n_items, lay->level[0].pitch, P.s[0].rows};
     std::lock_guard<std::mutex> guard(ctx->lk_mutex);
     klt_ctx::PyrScratch* slot = nullptr;
     for (auto& sc : ctx->pyr_scratch)
         if (sc.stream == stream && std::memcmp(sc.key, key, sizeof(key)) == 0) { slot = &sc; break; }
+    const size_t words = ((size_t)(n_cnt > 0 ? n_cnt : 0) + 1) / 2 * 2 + 2;   // counters, then (8-byte aligned) the 64-bit CTA count
     if (!slot) {
+        if (device_gen) return KLT_ERR_UNSUPPORTED;   // allocation cannot be captured: the caller gets one launch per level
         if (ctx->pyr_scratch.size() >= 64) {          // many geometries on many streams: recycle (rare; costs a sync)
             KLT_CUDA(cudaDeviceSynchronize());
             for (auto& sc : ctx->pyr_scratch) cudaFree(sc.cnt);
             ctx->pyr_scratch.clear();
         }
-        klt_ctx::PyrScratch fresh = {stream, nullptr, n_cnt, 0u, {key[0], key[1], key[2], key[3], key[4], key[5]}};
+        klt_ctx::PyrScratch fresh = {stream, nullptr, nullptr, n_cnt, 0u, {key[0], key[1], key[2], key[3], key[4], key[5]}};
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (size_t)(n_cnt > 0 ? n_cnt : 1) * sizeof(unsigned));
+        cudaError_t e = cudaMalloc(&p, 2 * words * sizeof(unsigned));
         if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? KLT_ERR_OUT_OF_MEMORY : (klt_status)e;
-        e = cudaMemset(p, 0, (size_t)(n_cnt > 0 ? n_cnt : 1) * sizeof(unsigned));
+        e = cudaMemset(p, 0, 2 * words * sizeof(unsigned));
         if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the memset is not ordered with non-blocking streams
         if (e != cudaSuccess) { cudaFree(p); return (klt_status)e; }
         fresh.cnt = static_cast<unsigned*>(p);
+        fresh.cnt_dev = fresh.cnt + words;
         try { ctx->pyr_scratch.push_back(fresh); } catch (const std::bad_alloc&) { cudaFree(p); return KLT_ERR_OUT_OF_MEMORY; }
         slot = &ctx->pyr_scratch.back();
     }
-    if (slot->gen >= 0x0fffffffu) {                   // counters would wrap: start over (once per 2.7e8 launches)
-        KLT_CUDA(cudaStreamSynchronize(stream));
-        KLT_CUDA(cudaMemset(slot->cnt, 0, (size_t)(slot->capacity > 0 ? slot->capacity : 1) * sizeof(unsigned)));
-        KLT_CUDA(cudaDeviceSynchronize());
-        slot->gen = 0;
+    // counters are monotonic modulo 2^32 and compared by difference: nothing is ever reset
+    if (device_gen) {
+        P.cnt = slot->cnt_dev;
+        P.gen = 0u;
+        P.done = reinterpret_cast<unsigned long long*>(slot->cnt_dev + words - 2);
+    } else {
+        P.cnt = slot->cnt;
+        P.gen = ++slot->gen;
+        P.done = nullptr;
     }
-    P.cnt = slot->cnt;
-    P.gen = ++slot->gen;
     if (reuse) { P.hash_new = reuse->hash_new; P.hash_old = reuse->hash_old; P.hash_clear = reuse->hash_clear; P.skipped = reuse->skipped; P.reuse_mask = reuse->mask; }
-    s = pyr_fused_launch(P, stream);
-    if (s != KLT_OK) --slot->gen;
+    s = pyr_fused_launch(P, device_gen, stream);
+    if (s != KLT_OK && !device_gen) --slot->gen;
     return s;
 }
 

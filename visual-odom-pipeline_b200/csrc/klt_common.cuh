@@ -73,7 +73,8 @@ struct PyrFused {
     int n_steps, batch;
     long long n_tasks;
     unsigned* cnt;      // completion counters, monotonic: a strip of launch number `gen` is complete at gen * tiles_x
-    unsigned gen;
+    unsigned gen;               // launch number on the counter array, from the host (ordinary launches)
+    unsigned long long* done;   // graph-safe form: CTAs finished in all launches on this counter array so far (gen - 1 = done / grid size)
     // Reuse of pyramids across calls of the host entry points (klt_capi.cu: track_host): item b is left as it is when
     // bit b of reuse_mask is set and the content hash of its freshly uploaded level 0 (hash_new, 2 words per item) equals
     // the hash of the image its levels were built from (hash_old).  hash_clear: 4 words zeroed for the call after next.
@@ -87,7 +88,7 @@ struct PyrFused {
 klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, uint8_t* const* dst, const int* w, const int* h,
                           const long long* spitch, const long long* sbatch, const long long* dpitch, const long long* dbatch,
                           int batch, int sm_count, long long* n_counters);
-klt_status pyr_fused_launch(const PyrFused& P, cudaStream_t stream);
+klt_status pyr_fused_launch(const PyrFused& P, bool device_gen, cudaStream_t stream);
 
 // Two pyramid levels (l -> l+1 -> l+2) in one launch; KLT_ERR_UNSUPPORTED for shapes it does not take.
 klt_status pyr_down2_launch(const uint8_t* src, int w0, int h0, long long pitch0, long long batch0,

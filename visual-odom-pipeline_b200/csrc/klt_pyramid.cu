@@ -789,19 +789,25 @@ klt_status launch_ring(const uint8_t* src, int w, int h, long long spitch, long 
 // tasks as pyr_down_ring_kernel; a task of step l >= 1 first waits until the strips of level l that hold its input rows
 // are complete: every producer task ends with fence + one atomicAdd on its (image, strip) counter, and a counter is
 // complete at gen * tiles_x (gen = launches so far on this counter array, so nothing is zeroed between launches).
+// gen comes from the host, or -- for launches recorded into a CUDA graph -- from a device-side count (see DEVGEN below).
 // Producers always have lower task indices than their consumers and CTAs are dispatched in index order, and a waiting
 // warp holds no resource a producer needs, so the wait cannot deadlock; it is bounded anyway.
 // Why: the small levels are launch- and tail-bound on their own (level 1 -> 2: 40 %, 2 -> 3: 18 % of the copy peak for
 // 310 KITTI frames, 3 x 4 us of launch latency for a single pair); in one grid they run in the shadow of level 0 -> 1.
-template <int MINB>
+template <int MINB, bool DEVGEN>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
 {
     extern __shared__ __align__(128) uint8_t ring_smem[];
+    __shared__ unsigned cta_done;   // finished tasks of this CTA (see sign_off)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (task >= P.n_tasks) return;  // warp-uniform; no block-level barriers in this kernel
+    if constexpr (DEVGEN) {
+        if (threadIdx.x == 0) cta_done = 0u;
+        __syncthreads();            // the only block-level barrier of the kernel: before any warp leaves
+    }
+    if (task >= P.n_tasks) return;  // warp-uniform
     int l = 0;
     while (l + 1 < P.n_steps && task >= P.s[l + 1].task_begin) ++l;
     const PyrStep& S = P.s[l];
@@ -812,6 +818,26 @@ pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
     const int b = (int)(t2 / S.strips_y);
     const int y0 = sy * S.rows;
     const int y1 = min(y0 + S.rows, S.dh);
+    // Number of this launch on the counter array.  Ordinary launches get it from the host (P.gen).  Launches recorded into a
+    // CUDA graph (DEVGEN) must not carry host-side state: they derive it from P.done, which counts the CTAs that have
+    // finished in ALL launches so far (64 bits: never wraps) -- every launch on this array has the same grid, the previous
+    // launches are complete when this one starts, and the count cannot reach the next multiple of the grid size while a task
+    // is still running, so done / gridDim.x is the number of completed launches for every task of this launch.  (Costs 3 %
+    // on the 310-image build, hence the two forms; they use separate counter arrays.)
+    unsigned gen = P.gen;
+    if constexpr (DEVGEN) {
+        if (l > 0) gen = (unsigned)(*reinterpret_cast<const volatile unsigned long long*>(P.done) / gridDim.x) + 1u;
+    }
+    // DEVGEN: tasks are counted per CTA in shared memory; the last warp of a CTA adds the CTA to the global count
+    auto sign_off = [&]() {
+        if constexpr (DEVGEN) {
+            if (lane == 0) {
+                const long long first = (long long)blockIdx.x * kWarpsPerBlock;
+                const unsigned cta_tasks = (unsigned)min((long long)kWarpsPerBlock, P.n_tasks - first);
+                if (atomicAdd(&cta_done, 1u) == cta_tasks - 1u) atomicAdd(P.done, 1ull);   // (only counted: the kernel boundary orders the data)
+            }
+        }
+    };
     if (P.hash_new != nullptr) {
         if (task == 0 && lane == 0) { P.hash_clear[0] = 0u; P.hash_clear[1] = 0u; P.hash_clear[2] = 0u; P.hash_clear[3] = 0u; }
         // unchanged image (same content hash as the one this item's levels were built from): leave the item alone.  All
@@ -821,6 +847,7 @@ pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
                 if (l + 1 < P.n_steps) atomicAdd(P.cnt + S.cnt_off + (long long)b * S.strips_y + sy, 1u);
                 if (l == 0 && tx == 0 && sy == 0 && P.skipped) atomicAdd(P.skipped, 1ull);
             }
+            sign_off();
             return;
         }
     }
@@ -828,7 +855,7 @@ pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
         const PyrStep& Q = P.s[l - 1];              // produced this step's source level
         const int s_lo = max(2 * y0 - 2, 0) / Q.rows;
         const int s_hi = min(min(2 * y1, S.h - 1) / Q.rows, Q.strips_y - 1);
-        const unsigned target = P.gen * (unsigned)Q.tiles_x;
+        const unsigned target = gen * (unsigned)Q.tiles_x;
         const volatile unsigned* c = P.cnt + Q.cnt_off + (long long)b * Q.strips_y;
         for (int k = s_lo + lane; k <= s_hi; k += 32) {
             int spins = 0;
@@ -848,6 +875,7 @@ pyr_build_fused_kernel(const __grid_constant__ PyrFused P)
         __syncwarp();
         if (lane == 0) atomicAdd(P.cnt + S.cnt_off + (long long)b * S.strips_y + sy, 1u);
     }
+    sign_off();
 }
 
 // strip height of one step: see launch_ring
@@ -1127,22 +1155,25 @@ klt_status pyr_fused_plan(PyrFused& P, int n_steps, const uint8_t* const* src, u
     }
     P.n_steps = n_steps; P.batch = batch; P.n_tasks = tasks;
     P.hash_new = nullptr; P.hash_old = nullptr; P.hash_clear = nullptr; P.skipped = nullptr; P.reuse_mask = 0u;
+    P.gen = 0u; P.done = nullptr;
     *n_counters = counters;
     return KLT_OK;
 }
 
-klt_status pyr_fused_launch(const PyrFused& P, cudaStream_t stream)
+klt_status pyr_fused_launch(const PyrFused& P, bool device_gen, cudaStream_t stream)
 {
     using RC = RingCfg<8>;
     static PerDeviceOnce configured;
     const int smem = RC::WARP_BYTES * kWarpsPerBlock;
     if (configured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(pyr_build_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pyr_build_fused_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pyr_build_fused_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (klt_status)e;
     }
     const long long blocks = (P.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return KLT_ERR_UNSUPPORTED;
-    pyr_build_fused_kernel<3><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
+    if (device_gen) pyr_build_fused_kernel<3, true><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
+    else pyr_build_fused_kernel<3, false><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(P);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KLT_OK : (klt_status)e;
 }
