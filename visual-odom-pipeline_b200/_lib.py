@@ -85,6 +85,8 @@ class KLTLibraryError(RuntimeError):
 def load():
     """Load libklt_b200.so and bind every declared symbol.  Raises if it has not been built."""
     global _lib
+    if _lib is not None:      # fast path, no lock: the reference is assigned once
+        return _lib
     with _lock:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
@@ -143,6 +145,9 @@ _contexts = {}
 
 
 def default_context(device=0):
+    ctx = _contexts.get(device)      # fast path, no lock: entries are only ever added
+    if ctx is not None:
+        return ctx
     with _lock:
         ctx = _contexts.get(device)
     if ctx is None:

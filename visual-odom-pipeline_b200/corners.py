@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import KLT_OK
-from .lk import _fail, _raise_status, error
+from .lk import _addr, _fail, _raise_status, error
 
 
 def _u8_image(img, name, func):
@@ -48,7 +48,7 @@ def cornerMinEigenVal(src, blockSize, dst=None, ksize=3, borderType=4, device=0)
     out = np.empty((h, w), np.float32)
     ctx = _lib.default_context(device)
     with ctx.lock:
-        rc = _lib.load().klt_corner_min_eigen_val_host(ctx.handle, img.ctypes.data, img.strides[0], w, h, blockSize, out.ctypes.data)
+        rc = _lib.load().klt_corner_min_eigen_val_host(ctx.handle, _addr(img), img.strides[0], w, h, blockSize, _addr(out))
     if rc != KLT_OK:
         _raise_status(rc, "cornerMinEigenVal")
     return out
@@ -83,15 +83,15 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=No
             _fail("_mask.empty() || (_mask.type() == CV_8UC1 && _mask.sameSize(_image)) in function 'goodFeaturesToTrack'")
         if mask.strides[1] != 1 or mask.strides[0] < w:
             mask = np.ascontiguousarray(mask)
-        mptr, mpitch = mask.ctypes.data, mask.strides[0]
+        mptr, mpitch = _addr(mask), mask.strides[0]
     cap = maxCorners if maxCorners > 0 else w * h   # candidates are distinct pixels
     out = np.empty((cap, 2), np.float32)
     n = ctypes.c_int(0)
     ctx = _lib.default_context(device)
     with ctx.lock:
-        rc = _lib.load().klt_good_features_to_track_host(ctx.handle, img.ctypes.data, img.strides[0], w, h, mptr, mpitch,
+        rc = _lib.load().klt_good_features_to_track_host(ctx.handle, _addr(img), img.strides[0], w, h, mptr, mpitch,
                                                          maxCorners, qualityLevel, minDistance, blockSize,
-                                                         out.ctypes.data, cap, ctypes.byref(n))
+                                                         _addr(out), cap, ctypes.byref(n))
     if rc != KLT_OK:
         _raise_status(rc, "goodFeaturesToTrack")
     if n.value == 0:
@@ -124,10 +124,10 @@ def detectNewFeatures(image, trackedPoints, maskRadius, maxCorners=1000, quality
     n = ctypes.c_int(0)
     ctx = _lib.default_context(device)
     with ctx.lock:
-        rc = _lib.load().klt_good_features_to_track_points_host(ctx.handle, img.ctypes.data, img.strides[0], w, h,
-                                                                pts.ctypes.data if len(pts) else None, len(pts), maskRadius,
+        rc = _lib.load().klt_good_features_to_track_points_host(ctx.handle, _addr(img), img.strides[0], w, h,
+                                                                _addr(pts) if len(pts) else None, len(pts), maskRadius,
                                                                 maxCorners, qualityLevel, minDistance, blockSize,
-                                                                out.ctypes.data, cap, ctypes.byref(n))
+                                                                _addr(out), cap, ctypes.byref(n))
     if rc != KLT_OK:
         _raise_status(rc, "detectNewFeatures")
     if n.value == 0:

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import KLT_OK
 from .corners import _u8_image
-from .lk import _fail, _raise_status, error
+from .lk import _addr, _fail, _raise_status, error
 
 BORDER_REFLECT_101 = 4   # cv2.BORDER_DEFAULT
 
@@ -37,8 +37,8 @@ def bilateralFilter(src, d, sigmaColor, sigmaSpace, dst=None, borderType=BORDER_
     h, w = img.shape
     out = np.empty((h, w), np.uint8)
     ctx = _lib.default_context(device)
-    rc = _lib.load().klt_bilateral_filter_host(ctx.handle, img.ctypes.data, img.strides[0], w, h, d, sigmaColor, sigmaSpace,
-                                               out.ctypes.data, out.strides[0])
+    rc = _lib.load().klt_bilateral_filter_host(ctx.handle, _addr(img), img.strides[0], w, h, d, sigmaColor, sigmaSpace,
+                                               _addr(out), out.strides[0])
     if rc != KLT_OK:
         _raise_status(rc, "bilateralFilter")
     return out

@@ -62,6 +62,37 @@ def make_params(winSize=(21, 21), criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), fl
     return klt_lk_params(win_w, win_h, ctype, ccount, ceps, int(flags), float(minEigThreshold))
 
 
+_PARAMS_CACHE = {}
+
+
+def _cached_params(win_w, win_h, criteria, flags, minEigThreshold):
+    """make_params with the struct cached per parameter set (the reference calls with the same parameters for every frame;
+    building a ctypes structure costs more than a microsecond).  The structs are only ever read."""
+    try:
+        key = (win_w, win_h, criteria[0], criteria[1], criteria[2], flags, minEigThreshold)
+        prm = _PARAMS_CACHE.get(key)
+    except Exception:
+        key, prm = None, None
+    if prm is None:
+        prm = make_params((win_w, win_h), criteria, flags, minEigThreshold)
+        if key is not None and len(_PARAMS_CACHE) < 256:
+            _PARAMS_CACHE[key] = prm
+    return prm
+
+
+_CHAR0 = ctypes.c_char * 0
+
+
+def _addr(arr):
+    """Address of a numpy array's first element.  arr.ctypes.data builds a helper object on every access (2 us; six of them
+    were most of the wrapper's cost); going through the buffer protocol takes a third of that.  Read-only or
+    non-contiguous arrays do not export a writable simple buffer: they take the slow way."""
+    try:
+        return ctypes.addressof(_CHAR0.from_buffer(arr))
+    except (TypeError, ValueError, BufferError):
+        return arr.ctypes.data
+
+
 def _host_image(img, name):
     if not isinstance(img, np.ndarray):
         _fail("%s is not a numpy array, neither a scalar" % name)
@@ -117,7 +148,7 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, status=None, e
     n = pts.shape[0]
     if n == 0:
         return None, None, None
-    params = make_params((win_w, win_h), criteria, flags, minEigThreshold)
+    params = _cached_params(win_w, win_h, criteria, flags, minEigThreshold)
     out = np.empty((n, 2), np.float32)
     if int(flags) & OPTFLOW_USE_INITIAL_FLOW:
         if nextPts is None:
@@ -130,12 +161,10 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, status=None, e
     er = np.empty((n, 1), np.float32)
     h, w = prev.shape
     ctx = _lib.default_context(device)
-    L = _lib.load()
-    with ctx.lock:
-        rc = L.klt_calc_optical_flow_pyr_lk_host(
-            ctx.handle, prev.ctypes.data, prev.strides[0], nxt.ctypes.data, nxt.strides[0], w, h,
-            pts.ctypes.data, out.ctypes.data, st.ctypes.data, er.ctypes.data, n, maxLevel,
-            ctypes.byref(params), None)
+    # (no Python-side lock: the *_host entry points of a context are serialised inside the library)
+    rc = _lib.load().klt_calc_optical_flow_pyr_lk_host(
+        ctx.handle, _addr(prev), prev.strides[0], _addr(nxt), nxt.strides[0], w, h,
+        _addr(pts), _addr(out), _addr(st), _addr(er), n, maxLevel, ctypes.byref(params), None)
     if rc != KLT_OK:
         _raise_status(rc, "calcOpticalFlowPyrLK")
     return out.reshape(shape), st, er
@@ -175,9 +204,9 @@ def trackBidirectional(prevImg, nextImg, prevPts, max_bidir_error=30, winSize=(3
     L = _lib.load()
     with ctx.lock:
         rc = L.klt_track_bidirectional_host(
-            ctx.handle, prev.ctypes.data, prev.strides[0], nxt.ctypes.data, nxt.strides[0], w, h, pts.ctypes.data, n,
+            ctx.handle, _addr(prev), prev.strides[0], _addr(nxt), nxt.strides[0], w, h, _addr(pts), n,
             maxLevel, ctypes.byref(params), float(max_bidir_error),
-            out.ctypes.data, st.ctypes.data, er.ctypes.data, keep.ctypes.data, bd.ctypes.data)
+            _addr(out), _addr(st), _addr(er), _addr(keep), _addr(bd))
     if rc != KLT_OK:
         _raise_status(rc, "trackBidirectional")
     return out.reshape(shape), keep.view(np.bool_), bd, st, er
@@ -205,8 +234,8 @@ def buildOpticalFlowPyramid(img, winSize, maxLevel, pyramid=None, withDerivative
         if rc != KLT_OK:
             _raise_status(rc, "buildOpticalFlowPyramid")
         buf = np.empty(offs[top.value + 1], np.uint8)
-        rc = L.klt_build_optical_flow_pyramid_host(ctx.handle, im.ctypes.data, im.strides[0], w, h, win_w, win_h,
-                                                   maxLevel, buf.ctypes.data, offs, ctypes.byref(top))
+        rc = L.klt_build_optical_flow_pyramid_host(ctx.handle, _addr(im), im.strides[0], w, h, win_w, win_h,
+                                                   maxLevel, _addr(buf), offs, ctypes.byref(top))
     if rc != KLT_OK:
         _raise_status(rc, "buildOpticalFlowPyramid")
     levels, lw, lh = [], w, h
