@@ -25,6 +25,19 @@ constexpr int kM = 3;  // margin of the staged next-image region
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kExact = 1 << 24;
 
+#ifdef KLT_LK_PHASES
+// diagnostics build (build.py --variant phases --extra -DKLT_LK_PHASES; scripts/lk_phases.py): cycles per phase of the
+// iteration loop of ONE selected point, stamped by its warp 0
+__device__ unsigned long long g_ph[16];
+__device__ long long g_ph_gid = -1;
+// ph_on is uniform over the warp (a per-lane condition makes the compiler split the lane's path off the warp's)
+#define PH(i) do { if (ph_on) { const long long c_ = clock64(); if (lane == 0) atomicAdd(&g_ph[i], (unsigned long long)(c_ - ph_t)); ph_t = clock64(); } } while (0)
+#define PH_COUNT(i) do { if (ph_on && lane == 0) atomicAdd(&g_ph[i], 1ull); } while (0)
+#else
+#define PH(i) do { } while (0)
+#define PH_COUNT(i) do { } while (0)
+#endif
+
 __host__ __device__ constexpr int r4(int v) { return (v + 3) / 4 * 4; }
 __host__ __device__ constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 
@@ -35,17 +48,20 @@ __host__ __device__ constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 template <int WW, int WH>
 struct Chains {
     static constexpr int NV = 8 * (WW / 8), TL = WW - NV;
+    static constexpr int OVER = 16;   // the chain loops request up to 4 groups of 4 words past the end of a chain (never used)
     // G scratch: 12 SIMD chains (3 sums x 4 lanes, one float product per pixel) of GQ4 floats, then 3 tail chains of
-    // GT4 floats (zero padded to multiples of 4), then 16 result words
+    // GT4 floats (zero padded to multiples of 4), OVER words, then 16 result words
     static constexpr int GQ = WH * (NV / 4), GT = WH * TL;
     static constexpr int GQ4 = (GQ + 3) / 4 * 4, GT4 = (GT + 3) / 4 * 4;
-    static constexpr int G_RES = 12 * GQ4 + 3 * GT4;
+    static constexpr int G_RES = 12 * GQ4 + 3 * GT4 + OVER;
     static constexpr int G_WORDS = G_RES + 16;
     // b scratch: 8 SIMD chains (2 sums x 4 lanes) of int pairs (x, x+4) in visiting order, then 2 tail chains of floats
+    // (zero padded), OVER words, then 12 result words: q[0..3] of b1, of b2, t of b1, of b2
     static constexpr int NS = NV / 8;                                // 8-pixel SIMD steps per window row
     static constexpr int SLEN = 2 * WH * NS;                         // ints per SIMD chain
+    static constexpr int SLEN4 = (SLEN + 3) / 4 * 4;                 // chain stride (the odd pair of an odd chain is zero padded)
     static constexpr int TLEN = (WH * TL + 3) / 4 * 4;               // floats per tail chain (zero padded)
-    static constexpr int B_RES = 8 * SLEN + 2 * TLEN;                // 12 result words: q[0..3] of b1, of b2, t of b1, of b2
+    static constexpr int B_RES = 8 * SLEN4 + 2 * TLEN + OVER;
     static constexpr int B_WORDS = (B_RES + 12 + 3) / 4 * 4;
 };
 
@@ -247,16 +263,54 @@ __device__ __forceinline__ int point_sum15_lane(const int (&v)[16], int* red16, 
     return mine;
 }
 
-// serial float32 sum of one zero-padded chain of n4 floats (n4 % 4 == 0), in order
-__device__ __forceinline__ float chain_sum(const float* __restrict__ p, int n4)
+// Serial float32 sum, in order, of one zero-padded chain of 4 * N4 floats.  The adds are one dependent chain (4 cycles
+// each), so the loads must never be waited for: three groups of 4 are always in flight in rotating registers (the last
+// requests read up to 3 groups past the chain -- the next chain or the OVER words -- and are dropped).
+__device__ __forceinline__ float add4(float acc, const float4 v)
+{
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+}
+template <int N4>
+__device__ __forceinline__ float chain_sum(const float* __restrict__ p)
 {
     const float4* __restrict__ src = reinterpret_cast<const float4*>(p);
+    constexpr int R = N4 / 3 * 3;
     float acc = 0.f;
-#pragma unroll 4
-    for (int e = 0; e < n4 / 4; ++e) {
-        const float4 v = src[e];
-        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+    float4 a = src[0], b = src[1], c = src[2];
+#pragma unroll 1
+    for (int e = 0; e < R; e += 3) {
+        acc = add4(acc, a); a = src[e + 3];
+        acc = add4(acc, b); b = src[e + 4];
+        acc = add4(acc, c); c = src[e + 5];
     }
+    if constexpr (N4 - R >= 1) acc = add4(acc, a);
+    if constexpr (N4 - R >= 2) acc = add4(acc, b);
+    return acc;
+}
+
+// The same for a chain of 2 * N4 int pairs: each pair is summed in int32 and converted (off the dependent chain) before
+// it is added; four groups of two pairs in flight.
+__device__ __forceinline__ float add2p(float acc, const int4 v)
+{
+    return __fadd_rn(__fadd_rn(acc, (float)(v.x + v.y)), (float)(v.z + v.w));
+}
+template <int N4>
+__device__ __forceinline__ float chain_sum_pairs(const int* __restrict__ p)
+{
+    const int4* __restrict__ src = reinterpret_cast<const int4*>(p);
+    constexpr int R = N4 / 4 * 4;
+    float acc = 0.f;
+    int4 a = src[0], b = src[1], c = src[2], d = src[3];
+#pragma unroll 1
+    for (int e = 0; e < R; e += 4) {
+        acc = add2p(acc, a); a = src[e + 4];
+        acc = add2p(acc, b); b = src[e + 5];
+        acc = add2p(acc, c); c = src[e + 6];
+        acc = add2p(acc, d); d = src[e + 7];
+    }
+    if constexpr (N4 - R >= 1) acc = add2p(acc, a);
+    if constexpr (N4 - R >= 2) acc = add2p(acc, b);
+    if constexpr (N4 - R >= 3) acc = add2p(acc, c);
     return acc;
 }
 
@@ -268,22 +322,27 @@ __device__ __forceinline__ void replay_g(float* __restrict__ gf, int wip, int la
     using CH = Chains<WW, WH>;
     constexpr int TW = WPP > 1 ? 1 : 0;
     if (wip == 0) {
-        const float acc = chain_sum(gf + (lane < 12 ? lane : 0) * CH::GQ4, CH::GQ4);
+        const float acc = chain_sum<CH::GQ4 / 4>(gf + (lane < 12 ? lane : 0) * CH::GQ4);
         if (lane < 12) gf[CH::G_RES + (lane >> 2) * 5 + (lane & 3)] = acc;   // result layout: [sum][q0 q1 q2 q3 t]
     }
     if (wip == TW) {
-        const float acc = chain_sum(gf + 12 * CH::GQ4 + (lane < 3 ? lane : 0) * CH::GT4, CH::GT4);
+        const float acc = chain_sum<CH::GT4 / 4>(gf + 12 * CH::GQ4 + (lane < 3 ? lane : 0) * CH::GT4);
         if (lane < 3) gf[CH::G_RES + lane * 5 + 4] = acc;
     }
 }
 
-// zero the padding of the two tail chains of one b scratch buffer
+// zero the padding of the chains of one b scratch buffer
 template <int WW, int WH, int NT>
 __device__ __forceinline__ void zero_pad_b(int* buf, int tid)
 {
     using CH = Chains<WW, WH>;
-    constexpr int PAD = CH::TLEN - WH * CH::TL;
-    if (tid < 2 * PAD) buf[8 * CH::SLEN + (tid / (PAD > 0 ? PAD : 1)) * CH::TLEN + WH * CH::TL + tid % (PAD > 0 ? PAD : 1)] = 0;
+    constexpr int PQ = CH::SLEN4 - CH::SLEN, PT = CH::TLEN - WH * CH::TL;
+    static_assert(8 * PQ + 2 * PT <= NT, "one pad word per thread");
+    if (tid < 8 * PQ) buf[(tid / (PQ > 0 ? PQ : 1)) * CH::SLEN4 + CH::SLEN + tid % (PQ > 0 ? PQ : 1)] = 0;
+    else if (tid < 8 * PQ + 2 * PT) {
+        const int t = tid - 8 * PQ;
+        buf[8 * CH::SLEN4 + (t / (PT > 0 ? PT : 1)) * CH::TLEN + WH * CH::TL + t % (PT > 0 ? PT : 1)] = 0;
+    }
 }
 
 // b replay, split over the point's warps: warp 0 runs the 8 SIMD chains (lane = chain; int pair -> float -> add), warp
@@ -294,23 +353,11 @@ __device__ __forceinline__ void replay_b(int* __restrict__ buf, int wip, int lan
     using CH = Chains<WW, WH>;
     constexpr int TW = WPP > 1 ? 1 : 0;
     if (wip == 0) {
-        const int2* __restrict__ src = reinterpret_cast<const int2*>(buf + (lane & 7) * CH::SLEN);
-        float acc = 0.f;
-#pragma unroll 6
-        for (int e = 0; e < CH::SLEN / 2; ++e) {
-            const int2 v = src[e];
-            acc = __fadd_rn(acc, (float)(v.x + v.y));
-        }
+        const float acc = chain_sum_pairs<CH::SLEN4 / 4>(buf + (lane & 7) * CH::SLEN4);
         if (lane < 8) reinterpret_cast<float*>(buf)[CH::B_RES + lane] = acc;
     }
     if (wip == TW) {
-        const float4* __restrict__ src = reinterpret_cast<const float4*>(buf + 8 * CH::SLEN + (lane & 1) * CH::TLEN);
-        float acc = 0.f;
-#pragma unroll 4
-        for (int e = 0; e < CH::TLEN / 4; ++e) {
-            const float4 v = src[e];
-            acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
-        }
+        const float acc = chain_sum<CH::TLEN / 4>(reinterpret_cast<const float*>(buf) + 8 * CH::SLEN4 + (lane & 1) * CH::TLEN);
         if (lane < 2) reinterpret_cast<float*>(buf)[CH::B_RES + 8 + lane] = acc;
     }
 }
@@ -339,17 +386,34 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
     int* red16 = reinterpret_cast<int*>(ws + C::OFF_R16);
     int par3 = 0, par16 = 0;
 
-    // units of this thread: unit u = tid + k*NT covers window pixels (y, x0..x0+3); coordinates are recomputed where
-    // needed (division by a constant), only the word offset inside the staged next-image region is kept.
-    auto unit_y = [&](int k) { const int u = tid + k * C::NT; return (u < C::NU ? u : 0) / C::UPR; };
-    auto unit_x0 = [&](int k) { const int u = tid + k * C::NT; const int uu = (u < C::NU ? u : 0); return 4 * (uu - (uu / C::UPR) * C::UPR); };
+    // units of this thread: unit u = tid + k*NT covers window pixels (y, x0..x0+3).  Only jw[k] = y * (SJ/4) + x0/4, the word
+    // offset inside the staged next-image region, is kept; y and x0 are decoded from it where needed (shift / mask when
+    // SJ/4 is a power of two -- the 21x21 window, where the division of u by UPR = 6 that this replaces was 5-8 % of all
+    // executed instructions -- else from u as before: UPR = 8 for the 31x31 window).
     auto unit_ok = [&](int k) { return tid + k * C::NT < C::NU; };
     int jw[C::UPT];
 #pragma unroll
-    for (int k = 0; k < C::UPT; ++k) jw[k] = (unit_y(k) * C::SJ + unit_x0(k)) >> 2;
+    for (int k = 0; k < C::UPT; ++k) {
+        const int u = tid + k * C::NT, uu = (u < C::NU ? u : 0), y = uu / C::UPR;
+        jw[k] = y * (C::SJ / 4) + (uu - y * C::UPR);
+    }
+    static_assert(C::UPR <= C::SJ / 4, "x0/4 must fit below the row stride");
+    constexpr bool kDecodeJw = ((C::SJ / 4) & (C::SJ / 4 - 1)) == 0;
+    auto unit_y = [&](int k) {
+        if constexpr (kDecodeJw) return jw[k] / (C::SJ / 4);
+        else { const int u = tid + k * C::NT; return (u < C::NU ? u : 0) / C::UPR; }
+    };
+    auto unit_x0 = [&](int k) {
+        if constexpr (kDecodeJw) return 4 * (jw[k] % (C::SJ / 4));
+        else { const int u = tid + k * C::NT; const int uu = (u < C::NU ? u : 0); return 4 * (uu - (uu / C::UPR) * C::UPR); }
+    };
 
     const long long t_start = clock64();
     int n_t1 = 0, n_t2 = 0;
+#ifdef KLT_LK_PHASES
+    const bool ph_on = (wip == 0) && (gid == g_ph_gid);
+    long long ph_t = 0;
+#endif
     const float2 p0 = reinterpret_cast<const float2*>(L.prev_pts)[gid];
     float2 outp = make_float2(0.f, 0.f);
     if (L.flags & KLT_OPTFLOW_USE_INITIAL_FLOW) outp = reinterpret_cast<const float2*>(L.next_pts)[gid];
@@ -630,6 +694,9 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
 
         float pdx = 0.f, pdy = 0.f;
         bool sticky = false, pads_zeroed = false;
+#ifdef KLT_LK_PHASES
+        ph_t = clock64();
+#endif
         for (int j = 0; j < L.max_count; ++j) {
             int inx, iny;
             if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
@@ -637,6 +704,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 break;
             }
             ++iters;
+            PH_COUNT(15);
             ensure_j(inx, iny);
             int v00, v01, v10, v11;
             q14_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), v00, v01, v10, v11);
@@ -644,6 +712,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             const uint32_t W1 = (uint32_t)(v10 & 0xffff) | ((uint32_t)v11 << 16);
             DiffStore<C::PACK> dd[C::UPT];
             int s1, s2, bnd;
+            PH(0);   // loop top: range test, region test, weights
             {
                 // invalid pixels carry gx = gy = gm = 0, so they drop out of all three sums without a select
                 const int cb = (iny - jy0) * C::SJ + (inx - jax);
@@ -676,6 +745,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
             // diverging points fail it every time, and they are the ones that bound the launch latency.
             float b1 = 0.f, b2 = 0.f;
             bool classes = sticky;
+            PH(1);   // per-pixel pass
             if (!sticky) {
                 // per-thread |bound| <= UPT*4*8160*4080 < 2^31 for UPT <= 8; clamped to kExact + 1 so that the point total
                 // (<= 128 * (2^24 + 1) < 2^32, compared as unsigned) cannot wrap and a clamped thread alone fails the test
@@ -690,6 +760,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     classes = true;
                 }
             }
+            PH(2);   // tier 0
             if (classes) {
                 // tier 1: per accumulation class (4 SIMD lanes + tail), bound in units of 16 (rounded up per pixel)
                 ++n_t1;
@@ -724,6 +795,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 const bool exact = __all_sync(kFull, !is_bound || ctot <= (kExact >> 4));
                 // leave sticky mode once the whole-window bound would pass again (converging point)
                 sticky = __reduce_add_sync(kFull, is_bound ? ctot : 0) > (kExact >> 4);
+                PH(3);   // tier 1 sums + tests
                 if (exact) {
                     const float f = (float)ctot;
                     b1 = combine5(__shfl_sync(kFull, f, 0), __shfl_sync(kFull, f, 1), __shfl_sync(kFull, f, 2), __shfl_sync(kFull, f, 3),
@@ -744,7 +816,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                         if (unit_ok(k)) {
                             const int y = unit_y(k), x0 = unit_x0(k);
                             if (x0 >= C::NV) {
-                                float* tf = reinterpret_cast<float*>(buf) + 8 * CH::SLEN + y * CH::TL + (x0 - C::NV);
+                                float* tf = reinterpret_cast<float*>(buf) + 8 * CH::SLEN4 + y * CH::TL + (x0 - C::NV);
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj)
                                     if (x0 + jj < WW) {
@@ -757,14 +829,20 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
                                     const int d = dd[k].get(jj);
-                                    si[jj * CH::SLEN] = d * pxs[k][jj].gx();
-                                    si[(4 + jj) * CH::SLEN] = d * pxs[k][jj].gy();
+                                    si[jj * CH::SLEN4] = d * pxs[k][jj].gx();
+                                    si[(4 + jj) * CH::SLEN4] = d * pxs[k][jj].gy();
                                 }
                             }
                         }
+                    PH(4);   // replay stores
                     point_sync<WPP>(bar);
+                    PH(5);   // barrier before the replay
                     replay_b<WW, WH, WPP>(buf, wip, lane);
+                    PH(6);   // warp 0's chains
                     point_sync<WPP>(bar);
+                    PH(7);   // barrier after the replay (= the tail chains of warp 1)
+                    PH_COUNT(14);
+                    static_assert(CH::B_RES % 4 == 0, "results are read with 128-bit loads");
                     const float4 r1 = *reinterpret_cast<const float4*>(buf + CH::B_RES);
                     const float4 r2 = *reinterpret_cast<const float4*>(buf + CH::B_RES + 4);
                     const float2 rt = *reinterpret_cast<const float2*>(buf + CH::B_RES + 8);
@@ -772,6 +850,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                     b2 = combine5(r2.x, r2.y, r2.z, r2.w, rt.y);
                 }
             }
+            PH(8);   // combine
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -790,6 +869,7 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
                 break;
             }
             pdx = dx; pdy = dy;
+            PH(9);   // solve + termination tests
         }
 
         // ---- err at level 0 ------------------------------------------------------------------------------------
@@ -893,3 +973,17 @@ klt_status lk_launch_fast(const LKLaunch& L, int sm_count, int forced_wpp, cudaS
 }
 
 }  // namespace klt
+
+#ifdef KLT_LK_PHASES
+extern "C" int klt_debug_lk_phase_select(long long gid)
+{
+    unsigned long long zero[16] = {};
+    cudaError_t e = cudaMemcpyToSymbol(klt::g_ph, zero, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(klt::g_ph_gid, &gid, sizeof(gid));
+    return (int)e;
+}
+extern "C" int klt_debug_lk_phase_read(unsigned long long* out16)
+{
+    return (int)cudaMemcpyFromSymbol(out16, klt::g_ph, 16 * sizeof(unsigned long long));
+}
+#endif
