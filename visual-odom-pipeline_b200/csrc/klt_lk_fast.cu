@@ -153,10 +153,11 @@ __device__ __forceinline__ void point_sync(int bar)
 
 __device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
 {
-    const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
-    w00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
-    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
-    w10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
+    // (x * y) * 2^14 == x * (y * 2^14) bit for bit: scaling by a power of two commutes with rounding (no under/overflow here)
+    const float oa = __fsub_rn(1.f, a), ob = __fmul_rn(__fsub_rn(1.f, b), 16384.f), bb = __fmul_rn(b, 16384.f);
+    w00 = __float2int_rn(__fmul_rn(oa, ob));
+    w01 = __float2int_rn(__fmul_rn(a, ob));
+    w10 = __float2int_rn(__fmul_rn(oa, bb));
     w11 = 16384 - w00 - w01 - w10;
 }
 
@@ -166,6 +167,14 @@ __device__ __forceinline__ bool floor_in_range(float x, float y, int win_w, int 
     ix = finite ? __float2int_rd(x) : INT_MIN;
     iy = finite ? __float2int_rd(y) : INT_MIN;
     return finite && !(ix < -win_w || ix >= lw || iy < -win_h || iy >= lh);
+}
+
+// The same for coordinates known to be finite: a conversion that saturates (|x| >= 2^31) still lands outside the range.
+__device__ __forceinline__ bool floor_in_range_finite(float x, float y, int win_w, int win_h, int lw, int lh, int& ix, int& iy)
+{
+    ix = __float2int_rd(x);
+    iy = __float2int_rd(y);
+    return !(ix < -win_w || ix >= lw || iy < -win_h || iy >= lh);
 }
 
 __device__ __forceinline__ float combine5(float q0, float q1, float q2, float q3, float t)
@@ -453,12 +462,13 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
         // ---- stage both neighbourhoods; the previous level's readers are done (barrier below) -------------
         point_sync<WPP>(bar);
-        int jax = 0, jy0 = 0, jx0 = 0;  // region origin: smem col 0 <-> image x = jax; window columns start at jx0
-        bool jvalid = false;
+        // region origin: smem col 0 <-> image x = jax; window columns start at jx0.  Nothing staged: an origin that no
+        // window position is near (window positions lie in (-2^30, 2^30))
+        int jax = 0, jy0 = INT_MIN / 2, jx0 = INT_MIN / 2;
         {
             int inx, iny;
             if (floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
-                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
+                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3;
                 stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
             }
         }
@@ -684,9 +694,10 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
         // ---- iterations ------------------------------------------------------------------------------------
         // make sure the staged next-image region covers the window at (inx, iny)
         auto ensure_j = [&](int inx, int iny) {
-            if (!jvalid || inx < jx0 || iny < jy0 || inx + WW + 1 > jx0 + C::JW || iny + WH + 1 > jy0 + C::JR) {
+            // covered <=> 0 <= inx - jx0 <= 2 kM and the same in y (the region is the window + 1 plus kM on every side)
+            if ((unsigned)(inx - jx0) > 2u * kM || (unsigned)(iny - jy0) > 2u * kM) {
                 point_sync<WPP>(bar);
-                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3; jvalid = true;
+                jx0 = inx - kM; jy0 = iny - kM; jax = jx0 & ~3;
                 stage<C::JR, C::SJ, C::NT>(jreg, lvJ, imgJ, jax, jy0, jx0 - jax, C::JW, tid);
                 point_sync<WPP>(bar);
             }
@@ -697,9 +708,15 @@ lk_fast_kernel(const __grid_constant__ LKLaunch L)
 #ifdef KLT_LK_PHASES
         ph_t = clock64();
 #endif
+        // The position is tested for NaN / inf once: inside the loop it is a position that passed the range test plus a
+        // finite step (|A| < 2^14, |b| < 2^15, 1/D <= 2^23), so it stays finite.
+        if (L.max_count > 0 && !((fabsf(nx) < 1.0e9f) && (fabsf(ny) < 1.0e9f))) {
+            if (level == 0) status = 0;
+            continue;
+        }
         for (int j = 0; j < L.max_count; ++j) {
             int inx, iny;
-            if (!floor_in_range(nx, ny, WW, WH, lw, lh, inx, iny)) {
+            if (!floor_in_range_finite(nx, ny, WW, WH, lw, lh, inx, iny)) {
                 if (level == 0) status = 0;
                 break;
             }
