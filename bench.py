@@ -66,25 +66,44 @@ def describe(wl_name, wl):
             % (wl["idx"], wl_name, wl["w"], wl["h"], wl["n"], wl["win"][0], wl["max_level"], tuple(wl["criteria"])))
 
 
-def host_pool(wl, count, seed0):
-    """`count` distinct (prev, next, pts) host triples.  A few base pairs are synthesised with the
-    SURVEY s8d generator and the rest are derived by cyclic shifts (distinct bytes at distinct
-    addresses is what matters for the cache behaviour)."""
+class HostPool(list):
+    """list of (prev, next, pts) host triples + `crop(i, extra_off)`: entry i moved `extra_off` more columns along its canvas"""
+    crop = None
+
+
+LEGACY_ROLL_POOL = False    # --legacy-roll-pool: the cyclic-shift pool of rounds 1-2, kept so that their numbers can be reproduced
+
+
+def host_pool(wl, count, seed0, max_extra_off=0):
+    """`count` distinct (prev, next, pts) host triples.  A few wide base pairs are synthesised with the SURVEY s8d generator
+    (texture + affine warp) and every entry is a CROP of one of them at its own column offset: distinct bytes at distinct
+    addresses for the cache behaviour, a different motion field per entry (the warp is about the canvas centre), and no
+    seam.  (Rounds 1-2 used cyclic shifts: np.roll puts a motion discontinuity inside the image, and the windows that
+    straddle it ran 60-77 iterations against 42 for the worst point of an unshifted pair -- the tail of every launch was
+    an artefact of the generator.)"""
     from visual_odom_pipeline_b200 import synth as S
     h, w, n = wl["h"], wl["w"], wl["n"]
     n_base = min(count, 4)
-    bases = [S.frame_pair(h, w, seed=seed0 + i) for i in range(n_base)]
-    pool = []
+    step = 37
+    per = -(-count // n_base)
+    canv = [S.frame_pair(h, w if LEGACY_ROLL_POOL else w + (per - 1) * step + max_extra_off, seed=seed0 + i) for i in range(n_base)]
+
+    def crop(i, extra_off=0):
+        a, b = canv[i % n_base]
+        off = (i // n_base) * step + extra_off
+        if LEGACY_ROLL_POOL:
+            return np.ascontiguousarray(np.roll(a, off, axis=1)), np.ascontiguousarray(np.roll(b, off, axis=1))
+        return np.ascontiguousarray(a[:, off:off + w]), np.ascontiguousarray(b[:, off:off + w])
+
+    pool = HostPool()
+    pool.crop = crop
     for i in range(count):
-        a, b = bases[i % n_base]
-        sh = (i // n_base) * 37
-        if sh:
-            a, b = np.roll(a, sh, axis=1), np.roll(b, sh, axis=1)
+        a, b = crop(i)
         if wl["n"] == 100014:
             p = S.grid_points(422, 237, h, w)
         else:
             p = S.uniform_points(n, h, w, seed=seed0 + 1000 + i)
-        pool.append((np.ascontiguousarray(a), np.ascontiguousarray(b), p))
+        pool.append((a, b, p))
     return pool
 
 
@@ -233,15 +252,15 @@ def run_malaga_seq(args, wl_name, wl):
     ctx = K.default_context(local_rank)
     h, w, n, n_frames = wl["h"], wl["w"], wl["n"], wl["frames"]
     lkp = dict(winSize=wl["win"], maxLevel=wl["max_level"], criteria=wl["criteria"])
-    # 500 distinct frames: a base sequence of 25 frames (each a small warp of the previous one), replayed forwards and
-    # backwards with cyclic column shifts so that every frame of the run has different bytes from its neighbours
-    base = S.sequence(h, w, 25, seed=21 + rank)
+    # 500 distinct frames: a base sequence of 25 wide frames (each a small warp of the previous one), replayed forwards
+    # and backwards, every replay cropped 29 columns further along the canvas (distinct bytes, no seam: see host_pool)
     order = list(range(25)) + list(range(23, 0, -1))
+    base = S.sequence(h, w + (n_frames // len(order) + 1) * 29, 25, seed=21 + rank)
 
     def frame(i):
         f = base[order[i % len(order)]]
         sh = (i // len(order)) * 29
-        return np.roll(f, sh, axis=1) if sh else f
+        return f[:, sh:sh + w]
 
     def fresh_points(seed):
         p = S.uniform_points(n, h, w, seed=seed).astype(np.float32)
@@ -352,11 +371,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=0, help="distinct device-resident pairs (0 = enough to exceed L2)")
+    ap.add_argument("--legacy-roll-pool", action="store_true",
+                    help="build the pool from cyclic column shifts as rounds 1-2 did (seam inside every shifted image); default: crops of wide canvases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-detection", action="store_true", help="skip the Shi-Tomasi detection section (SURVEY s8f rank 2)")
     ap.add_argument("--no-sharded-batch", action="store_true", help="skip the configs[3] section (256 sharded sequences)")
     ap.add_argument("--sequences", type=int, default=256, help="configs[3]: independent sequences over all ranks")
     args = ap.parse_args()
+    global LEGACY_ROLL_POOL
+    LEGACY_ROLL_POOL = bool(args.legacy_roll_pool)
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.warmup < 3:
         args.warmup = 3
@@ -399,15 +422,16 @@ def main():
     layB.level[0].pitch = pitch
     layB.level[0].batch_stride = pitch * h
     n_host = min(P, 16)
-    hp = host_pool(wl, n_host, seed0=7 + 100 * rank)
+    dev_step = 53                                    # device entry i = host entry i % n_host, dev_step * (i // n_host) columns further
+    hp = host_pool(wl, n_host, seed0=7 + 100 * rank, max_extra_off=((P - 1) // n_host) * dev_step)
     imgs = torch.empty((2 * P, h, pitch), dtype=torch.uint8, device=dev)
     pyrs = torch.empty(max(int(layB.bytes), 1), dtype=torch.uint8, device=dev)
     pts = torch.empty((P, n, 2), dtype=torch.float32, device=dev)
     for i in range(P):
-        a, b, p = hp[i % n_host]
-        sh = (i // n_host) * 53
-        imgs[2 * i, :, :w].copy_(torch.from_numpy(np.roll(a, sh, axis=1) if sh else a))
-        imgs[2 * i + 1, :, :w].copy_(torch.from_numpy(np.roll(b, sh, axis=1) if sh else b))
+        a, b = hp.crop(i % n_host, (i // n_host) * dev_step)
+        p = hp[i % n_host][2]
+        imgs[2 * i, :, :w].copy_(torch.from_numpy(a))
+        imgs[2 * i + 1, :, :w].copy_(torch.from_numpy(b))
         pts[i].copy_(torch.from_numpy(p.reshape(n, 2)))
     out_q = torch.empty((P, n, 2), dtype=torch.float32, device=dev)
     out_s = torch.empty((P, n), dtype=torch.uint8, device=dev)
@@ -695,10 +719,9 @@ def main():
         try:
             import cv2
             i = args.warmup % P
-            a, b, p = hp[i % n_host]
-            sh = (i // n_host) * 53
-            a2, b2 = (np.roll(a, sh, axis=1), np.roll(b, sh, axis=1)) if sh else (a, b)
-            rq, rs, re_ = cv2.calcOpticalFlowPyrLK(np.ascontiguousarray(a2), np.ascontiguousarray(b2), p, None, winSize=win, maxLevel=max_level,
+            p = hp[i % n_host][2]
+            a2, b2 = hp.crop(i % n_host, (i // n_host) * dev_step)
+            rq, rs, re_ = cv2.calcOpticalFlowPyrLK(a2, b2, p, None, winSize=win, maxLevel=max_level,
                                                    criteria=wl["criteria"])
             gq, gs = out_q[i].cpu().numpy(), out_s[i].cpu().numpy()
             both = (rs.ravel() == 1) & (gs == 1)
@@ -731,6 +754,10 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": describe(wl_name, wl),
                        "l2": "rotating pool of %d distinct device-resident pairs (%.0f MB) > 126 MB L2; no flush needed" % (P, P * pair_bytes / 1e6),
+                       "pool": ("cyclic column shifts of 4 base pairs (the pool of rounds 1-2: a wrap-around seam inside every shifted image), %d point sets" % n_host)
+                               if LEGACY_ROLL_POOL else
+                               ("every pair is a crop of a wide synthetic canvas (texture + affine warp) at its own offset, %d point sets; "
+                                "no wrap-around seams" % n_host),
                        "sharding": "each rank tracks its own independent sequences; no collective on the data path",
                        "host_cores_per_rank": len(host_cores)},
             "timing": {"blocks": n_blocks, "steps_per_block": K_steps, "block_ms": block_ms,
@@ -780,11 +807,11 @@ def run_sharded_batch(args, wl, rank, local_rank, world, dev):
     n_seq, n_frames = args.sequences, 4
     lo, hi = sharding.shard_range(n_seq, world, rank)
     B = hi - lo
-    base = S.sequence(h, w, n_frames, seed=91)
+    base = S.sequence(h, 2 * w, n_frames, seed=91)
 
-    def host_frames(seq):     # deterministic per sequence id, on any rank
+    def host_frames(seq):     # deterministic per sequence id, on any rank: a crop of the wide base sequence (no seam)
         sh = (seq * 17) % w
-        return [np.roll(f, sh, axis=1) if sh else f for f in base]
+        return [np.ascontiguousarray(f[:, sh:sh + w]) for f in base]
 
     def host_points(seq):
         return S.uniform_points(n, h, w, seed=7000 + seq).reshape(n, 2)

@@ -13,19 +13,26 @@ if mode in ("all", "lk"):
     for _ in range(3):
         K.calcOpticalFlowPyrLK(a, b, p, None, winSize=win, maxLevel=3, criteria=(3, 30, 0.01))
 if mode in ("all", "pyr", "batch"):
-    B = 310
-    base = [S.texture(376, 1241, seed=s).astype(np.uint8) for s in range(4)]
-    imgs = T.alloc_image_batch(B, 376, 1241)
-    for i in range(B):
-        imgs[i].copy_(torch.from_numpy(np.roll(base[i % 4], 31 * (i // 4), axis=1)))
+    # 155 KITTI-sized pairs = 310 images, as bench.py's pool: crops of wide synthetic canvases at their own offsets
+    P = 155
+    canv = [S.frame_pair(376, 1241 + 31 * (P // 4), seed=7 + s) for s in range(4)]
+    imgs = T.alloc_image_batch(2 * P, 376, 1241)
+    prev, nxt_imgs = T.alloc_image_batch(P, 376, 1241), T.alloc_image_batch(P, 376, 1241)
+    for i in range(P):
+        off = 31 * (i // 4)
+        a = torch.from_numpy(np.ascontiguousarray(canv[i % 4][0][:, off:off + 1241]))
+        b = torch.from_numpy(np.ascontiguousarray(canv[i % 4][1][:, off:off + 1241]))
+        imgs[2 * i].copy_(a); imgs[2 * i + 1].copy_(b)
+        prev[i].copy_(a); nxt_imgs[i].copy_(b)
     torch.cuda.synchronize()
     pyr = T.DevicePyramid(imgs, win, 3)
     for _ in range(2):
         pyr.build()
     torch.cuda.synchronize()
     if mode in ("all", "batch"):
-        nxt = T.DevicePyramid(imgs.roll(1, 0).contiguous() if False else imgs, win, 3)
-        pts = torch.from_numpy(np.stack([S.uniform_points(2000, 376, 1241, seed=i).reshape(-1, 2) for i in range(8)])).cuda()
-        pts = pts.repeat(B // 8 + 1, 1, 1)[:B].contiguous()
-        T.lk_track(pyr, nxt, pts)
+        p0, p1 = T.DevicePyramid(prev, win, 3), T.DevicePyramid(nxt_imgs, win, 3)
+        pts = torch.from_numpy(np.stack([S.uniform_points(2000, 376, 1241, seed=1007 + i).reshape(-1, 2) for i in range(16)])).cuda()
+        pts = pts.repeat(P // 16 + 1, 1, 1)[:P].contiguous()
+        torch.cuda.synchronize()
+        T.lk_track(p0, p1, pts, criteria=(3, 30, 0.03 if win[0] == 31 else 0.01))
         torch.cuda.synchronize()
