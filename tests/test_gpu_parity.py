@@ -161,6 +161,19 @@ def test_lk_team_sizes_bit_exact(klt, wpp):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_lk_one_pass_grid_bit_exact(klt):
+    """Single-pair launches of the 4-warp shape dispatch the points near the image border first (a grid that holds every
+    point twice); KLT_LK_TWO_PASS=0 is the plain grid.  Both orders must give cv2's bits -- the default order is what
+    every other test of this file runs."""
+    import os, subprocess, sys
+    e = dict(os.environ)
+    e["KLT_LK_TWO_PASS"] = "0"
+    e["KLT_LK_WPP"] = "4"
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lk_variant_check.py")], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_lk_point_layouts_and_special_points(klt, cv2):
     a, b = S.frame_pair(120, 160, seed=2)
     base = S.uniform_points(40, 120, 160, seed=9)
