@@ -41,6 +41,9 @@ def run(h, w, B, win=(21, 21), max_level=3, reps=20):
     print(f"{w}x{h} B={B}: level0->1 {m1*1e3:.1f} us = {b01/m1/1e6:.0f} GB/s ({b01/m1/1e6/PEAK*100:.1f}% of measured {PEAK:.0f}); "
           f"whole pyramid ({pyr.top} levels) {m2*1e3:.1f} us = {ball/m2/1e6:.0f} GB/s ({ball/m2/1e6/PEAK*100:.1f}%); bit-exact={ok}", flush=True)
 
+if "single" in sys.argv:      # the single-pair shape only (latency of the one-launch build; env switches: DESIGN s10)
+    run(376, 1241, 2, reps=100)
+    sys.exit(0)
 run(376, 1241, 310)
 run(376, 1241, 2)
 run(480, 640, 600)
