@@ -105,7 +105,7 @@ typedef struct klt_lk_params {
     int32_t crit_type;      /* KLT_TERM_COUNT | KLT_TERM_EPS, as in cv2's criteria[0] */
     int32_t crit_max_count; /* criteria[1] */
     double crit_eps;        /* criteria[2] */
-    int32_t flags;          /* KLT_OPTFLOW_* */
+    int32_t flags;          /* KLT_OPTFLOW_*; every other bit must be 0 (0x100 / 0x200 are used by diagnostics and the launcher) */
     double min_eig_threshold; /* cv2 default 1e-4 */
 } klt_lk_params;
 
