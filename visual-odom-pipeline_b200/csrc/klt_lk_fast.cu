@@ -374,7 +374,10 @@ __device__ __forceinline__ void replay_b(int* __restrict__ buf, int wip, int lan
 }
 
 template <int WW, int WH, int WPP>
-__global__ void __launch_bounds__(kThreads, (WPP == 4 ? 5 : (WPP == 2 ? 4 : 3)))
+// CTAs per SM.  4-warp shape, 21x21: 7 (72 registers, no spills) -- with the launch no longer ending in a tail of long
+// points the bulk is issue-bound and more resident warps fill more slots (single pair 65.1 -> 64.5 us, four streams
+// 50.1 -> 44.6 us per pair; 8 CTAs spill: 72.1 us); 31x31: 5 (6 spill: 98 -> 106 us).
+__global__ void __launch_bounds__(kThreads, (WPP == 4 ? (WW * WH <= 21 * 21 ? 7 : 5) : (WPP == 2 ? 4 : 3)))
 lk_fast_kernel(const __grid_constant__ LKLaunch L)
 {
     using C = Cfg<WW, WH, WPP>;
